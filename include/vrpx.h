@@ -1,0 +1,188 @@
+/*
+ * vrpx.h — C ABI of the B200-native VRP-Gym rollout path (libvrpx.so).
+ *
+ * The reference (kevin-schumann/VRP-GYM) is pure Python: it has no FFI.  Its
+ * boundary is the Python class surface.  This ABI sits directly
+ * underneath that surface; every entry point cites the reference code it
+ * replaces (paths relative to the reference root).  All pointers are DEVICE
+ * pointers unless named h_*; all buffers are caller-owned; `stream` is a
+ * cudaStream_t passed as void*.  Every call returns 0 or a negative
+ * vrpx_status, never throws, never exits, and does not synchronise unless
+ * documented.  Build: nvcc -gencode arch=compute_100a,code=sm_100a.
+ */
+#ifndef VRPX_H
+#define VRPX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VRPX_API __attribute__((visibility("default")))
+#else
+#define VRPX_API
+#endif
+
+#define VRPX_ABI_VERSION 1
+#define VRPX_MAX_NODES 128 /* visited bitmask = 4 x u32 per instance */
+#define VRPX_EMB 128       /* embedding width E (graph_tsp_agent.py:98) */
+#define VRPX_HEADS 8       /* heads (graph_tsp_agent.py:101, :55) */
+#define VRPX_FF 512        /* encoder FF width (graph_tsp_agent.py:99) */
+#define VRPX_LAYERS 3      /* encoder layers (graph_tsp_agent.py:100) */
+
+typedef enum vrpx_status {
+  VRPX_OK = 0,
+  VRPX_ERR_ARG = -1,     /* bad argument (NULL, N > VRPX_MAX_NODES, ...) */
+  VRPX_ERR_DEVICE = -2,  /* not an sm_100 device / no device */
+  VRPX_ERR_CUDA = -3,    /* CUDA runtime error, see vrpx_last_error() */
+  VRPX_ERR_UNSUPPORTED = -4
+} vrpx_status;
+
+typedef enum vrpx_kind { VRPX_TSP = 0, VRPX_VRP = 1, VRPX_IRP = 2 } vrpx_kind;
+
+/* Device-resident SoA state of a batch of routing instances.
+ * Replaces: VRPNetwork/VRPGraph storage (gym_vrp/graph/vrp_network.py:9-42,
+ * vrp_graph.py:27-45) and the env fields visited/current_location/load/demands
+ * (gym_vrp/envs/tsp.py:162-174, irp.py:47,157-185). */
+typedef struct vrpx_env {
+  int32_t kind;      /* vrpx_kind */
+  int32_t N;         /* nodes per instance, 2..VRPX_MAX_NODES */
+  int64_t B;         /* instances */
+  double* xy;        /* [B][N][2] f64 coordinates */
+  int32_t* depot;    /* [B] */
+  double* demand;    /* [B][N] f64 (depot 0); may be NULL for TSP/VRP */
+  uint32_t* visited; /* [B][4] bit n = visited[n] AFTER the mask rules R1-R3 */
+  uint32_t* mask;    /* [B][4] decoder-visible mask: IRP = visited | (demand-load>0) (irp.py:151-155);
+                        TSP/VRP: must alias `visited` */
+  int32_t* cur;      /* [B] current_location */
+  double* load;      /* [B] f64 vehicle load (IRP; still required, unused for TSP/VRP) */
+} vrpx_env;
+
+VRPX_API int vrpx_abi_version(void);
+VRPX_API const char* vrpx_last_error(void); /* thread-local message of the last failing call */
+VRPX_API int vrpx_device_check(int device); /* <0 unless compute capability 10.x */
+
+/* Philox4x32-10 instance generator (throughput mode; NOT numpy-seed compatible).
+ * Fills xy (U[0,1)^2), depot (uniform), demand (U[1,10)/C, depot 0) following the
+ * distributions of vrp_graph.py:29,34,41-43.  Instance b uses counter (offset + b). */
+VRPX_API int vrpx_env_generate(const vrpx_env* env, uint64_t seed, uint64_t offset, void* stream);
+
+/* Episode reset: visited=0, cur=depot, load=1, then mask rules (tsp.py:158-160,167-174; irp.py:183-185). */
+VRPX_API int vrpx_env_reset(const vrpx_env* env, void* stream);
+
+/* One environment transition for all B instances = TSPEnv.step / IRPEnv.step
+ * (tsp.py:60-101, irp.py:49-99) fused with generate_mask (tsp.py:131-148, vrp.py:13-37,
+ * irp.py:126-155), is_done (tsp.py:103-104) and get_distances (vrp_network.py:59-78).
+ *   actions  [B] int64 (the (B,1) array of the reference, flattened)
+ *   reward   [B] f64, = -euclidean distance (tsp.py:98)
+ *   not_done [1] int32, must be zeroed by the caller; incremented (by >= 1) iff some instance is
+ *            not fully visited BEFORE the mask rules -> done == (*not_done == 0).
+ *   state    optional [B][N][4|5] f64 observation (tsp.py:106-129, irp.py:101-124), or NULL. */
+VRPX_API int vrpx_env_step(const vrpx_env* env, const int64_t* actions, double* reward, int32_t* not_done,
+                  double* state, void* stream);
+
+/* Observation / mask / visited materialised in the reference layout (get_state, generate_mask).
+ * state [B][N][4] = [x,y,is_depot,mask]; IRP [B][N][5] = [x,y,demand,is_depot,mask].
+ * mask/visited [B][N] f64 of 0/1.  Any output may be NULL. */
+VRPX_API int vrpx_env_observe(const vrpx_env* env, double* state, double* mask, double* visited, void* stream);
+
+/* Write back a (B,N) f64 0/1 array into the bitmask (used when a caller assigns env.visited). */
+VRPX_API int vrpx_env_set_visited(const vrpx_env* env, const double* visited, void* stream);
+
+/* ---------------------------------------------------------------- policy */
+
+/* Encoder parameters, torch layouts (row-major [out][in]) — state_dict keys of SURVEY App. A.5. */
+typedef struct vrpx_encoder_layer {
+  const float *in_proj_w, *in_proj_b;   /* [384][128], [384]  attention_layer.in_proj_* */
+  const float *out_proj_w, *out_proj_b; /* [128][128], [128] */
+  const float *bn1_w, *bn1_b;           /* [128] affine */
+  float *bn1_mean, *bn1_var;            /* [128] running stats (updated in train mode) */
+  const float *ff0_w, *ff0_b;           /* [512][128], [512] */
+  const float *ff2_w, *ff2_b;           /* [128][512], [128] */
+  const float *bn2_w, *bn2_b;
+  float *bn2_mean, *bn2_var;
+} vrpx_encoder_layer;
+
+typedef struct vrpx_encoder_weights {
+  int32_t f;                              /* node feature count: 2 (TSP/VRP) or 3 (IRP) */
+  const float *node_w, *node_b;           /* [128][f], [128]   encoder.node_embed */
+  const float *depot_w, *depot_b;         /* [128][2], [128]   encoder.depot_embed, or NULL (TSP) */
+  vrpx_encoder_layer layer[VRPX_LAYERS];
+} vrpx_encoder_weights;
+
+/* Bytes of scratch `ws` needed by vrpx_encoder_forward for R = B*N rows. */
+VRPX_API int64_t vrpx_encoder_workspace_bytes(int64_t B, int32_t N);
+
+/* GraphEncoder.forward / GraphDemandEncoder.forward (agents/graph_encoder.py:41-58, :95-138)
+ * with MultiHeadAttentionLayer (:183-198) and BatchNorm (:141-154).
+ *   x      [B][N][f] f32 node features, or NULL to read them from `env` (xy [, demand]) cast to f32
+ *          exactly as graph_tsp_agent.py:72 does;
+ *   depot  [B] int32 depot node per instance, or NULL (TSP: no depot embedding);
+ *   train  0: running statistics; 1: batch statistics over all B*N rows + running-stat update
+ *          (momentum 0.1, unbiased variance), graph_encoder.py:150-154;
+ *   h      [B][N][128] f32 output embeddings;
+ *   gemm_path 0: tcgen05 3xTF32 tensor-core GEMMs; 1: fp32 SIMT GEMMs (debug / cross-check). */
+VRPX_API int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, const float* x,
+                         const int32_t* depot, int64_t B, int32_t N, int32_t train, float* h, void* ws,
+                         int64_t ws_bytes, int32_t gemm_path, void* stream);
+
+/* Decoder parameters after host-side packing (agents/graph_decoder.py:29-44); vrpx/packing.py derives
+ * each array from the state_dict (in float64, rounded once to f32).  With W_q/W_k/W_v/b_* the in-projections of
+ * decoder.attention, W_o its out_proj, W_ao = _att_output, W_kp = _kp, W_ctx = _context_proj, and
+ * Kd = blockdiag_h(W_k,h^T)/sqrt(48)  (1024 x 384; folds the per-head key projection into the query):
+ *   ag_t  [128][1024]  (Kd · W_q[:, graph-embedding block])^T      IRP: W_q := W_q · W_ctx
+ *   af_t  [128][1024]  same for the `first` block (TSP/VRP only, NULL for IRP)
+ *   al_t  [128][1024]  same for the `last` block
+ *   a_c   [1024]       Kd · b_q
+ *   a_q0  [1024]       step-0 term of the learned placeholders _first_node / _last_node
+ *   a_load[1024]       IRP only: Kd · W_q · W_ctx[:, 256]   (multiplied by the f32 vehicle load)
+ *   m_t   [1024][128]  row h*128+d: (W_kp^T · W_ao · W_o[:, head h] · W_v,h)[:, d] / sqrt(128)
+ *   m_c   [128]        W_kp^T · W_ao · (W_o · b_v + b_o) / sqrt(128)
+ * The key bias b_k shifts every score of a head equally and cancels in the softmax. */
+typedef struct vrpx_decoder_weights {
+  const float *ag_t, *af_t, *al_t, *a_c, *a_q0, *a_load;
+  const float *m_t, *m_c;
+} vrpx_decoder_weights;
+
+typedef enum vrpx_rollout_mode { VRPX_GREEDY = 0, VRPX_SAMPLE = 1, VRPX_TEACHER = 2 } vrpx_rollout_mode;
+
+VRPX_API int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N);
+
+/* The rollout loop TSPModel/VRPModel/IRPModel.forward (agents/graph_tsp_agent.py:78-92,
+ * graph_vrp_agent.py:69-83, graph_irp_agent.py:82-105) with GraphDecoder.forward
+ * (agents/graph_decoder.py:51-115) and the env transition fused, all steps in ONE persistent
+ * cooperative launch.  The env must be in its reset state; on return it holds the terminal state.
+ *   h        [B][N][128] encoder output
+ *   mode     greedy argmax (graph_decoder.py:103), Philox sampling (:105-107), or teacher-forced
+ *   coupling glimpse-mask coupling group G (graph_decoder.py:93 `mask.repeat(H,1)`): attention row (b,h)
+ *            adds mask[g0 + ((b-g0)*8+h) mod G], g0 = floor(b/G)*G.  G == B is the reference at batch B;
+ *            0 disables the quirk's scrambling (adds the instance's own mask) — NOT reference-equal.
+ *   tape     [Tmax][B] uint8 actions: written (greedy/sample) or read (teacher); may be NULL unless teacher
+ *   t_begin  first step to execute: 0 starts an episode (builds the per-episode tables in `ws`); > 0 resumes
+ *            one whose `ws`, env state, logp and cost were left by the previous call (single-step decoding)
+ *   Tmax     maximum number of steps to run in this call = rows of `tape`/`logits` (row 0 = step t_begin)
+ *   logp     [B] f32 sum of log-probs (0 for greedy, graph_decoder.py:100)
+ *   cost     [B] f32 = -(acc_loss): f32 accumulation of f32(reward) in step order (graph_tsp_agent.py:85)
+ *   steps    [1] int32 number of steps executed (env.step_count)
+ *   logits   optional [Tmax][B][N] f32 dump of the masked pointer logits (tests), or NULL
+ *   seed/offset  Philox key / global instance-id offset (shard-invariant sampling)            */
+VRPX_API int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float* h, int32_t mode,
+                 int64_t coupling, uint64_t seed, uint64_t offset, uint8_t* tape, int32_t t_begin, int32_t Tmax,
+                 float* logp, float* cost, int32_t* steps, float* logits, void* ws, int64_t ws_bytes,
+                 void* stream);
+
+/* Test hook (tests/test_gemm.py): Y[R][NOUT] = epilogue(X[R][K] · W[NOUT][K]^T) through the tcgen05 3xTF32
+ * path (path 0) or the fp32 SIMT path (path 1); epilogue = +bias, ReLU, +residual, *scale+shift (each optional). */
+VRPX_API int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float* W, int32_t NOUT, const float* bias,
+                             int32_t relu, const float* residual, const float* scale, const float* shift, float* Y,
+                             int32_t path, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+VRPX_API int64_t vrpx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRPX_H */

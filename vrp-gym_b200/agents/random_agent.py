@@ -1,0 +1,33 @@
+"""RandomAgent — uniformly random feasible actions (reference agents/random_agent.py:6-41).
+
+The action stream is the legacy global numpy generator consumed instance by instance
+(`np.random.choice(feasible, 1)`), which is inherently sequential; it therefore stays on the host so that
+equal seeds give the reference's exact tours.  Transitions, distances and masks come from the CUDA env."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+class RandomAgent(nn.Module):
+    def __init__(self, seed: int = 69):
+        super().__init__()
+        np.random.seed(seed)
+
+    def forward(self, env) -> torch.Tensor:
+        state = env.get_state()
+        if isinstance(state, tuple):  # IRPEnv
+            state = state[0]
+        done = False
+        acc_loss = torch.zeros(size=(state.shape[0],))
+        while not done:
+            if isinstance(state, tuple):
+                state = state[0]
+            mask = state[:, :, -1]
+            actions = np.empty((mask.shape[0],), dtype=np.int64)
+            for i in range(mask.shape[0]):
+                actions[i] = np.random.choice(np.flatnonzero(mask[i] == 0), 1)[0]
+            state, loss, done, _ = env.step(actions[:, None])
+            acc_loss += torch.tensor(loss, dtype=torch.float)  # f32 accumulation, as the reference
+        return acc_loss

@@ -1,0 +1,27 @@
+// gemm.cuh — internal GEMM interface shared by the SIMT cross-check path (encoder.cu) and the
+// tcgen05 3xTF32 tensor-core path (gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace vrpx {
+
+// Y[R][NOUT] = epilogue( X[R][K] · W[NOUT][K]^T )      (W in torch nn.Linear layout)
+// epilogue order: acc + bias -> relu -> + residual -> * scale + shift
+struct GemmArgs {
+  const float* X;
+  int64_t R;
+  int K;
+  const float* W;
+  int NOUT;
+  const float* bias;      // [NOUT] or nullptr
+  int relu;
+  const float* residual;  // [R][NOUT] or nullptr
+  const float* scale;     // [NOUT] or nullptr  (eval-mode BatchNorm folded affine)
+  const float* shift;     // [NOUT] or nullptr
+  float* Y;
+};
+
+int gemm_simt(const GemmArgs& a, cudaStream_t stream);  // fp32 FFMA, smem tiled
+int gemm_tc(const GemmArgs& a, cudaStream_t stream);    // tcgen05.mma kind::tf32, 3-term split (≈fp32)
+
+}  // namespace vrpx
