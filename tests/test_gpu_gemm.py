@@ -1,0 +1,71 @@
+"""GPU parity of the two GEMM paths behind the encoder (csrc/gemm_tc.cu tcgen05 3xTF32, csrc/encoder.cu SIMT)
+against a float64 torch matmul, through the C ABI test hook vrpx_debug_gemm."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(path, R, K, NOUT, bias, relu, residual, bn, seed=0):
+    import vrpx
+
+    dev = vrpx.require_device()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    X = torch.randn(R, K, generator=g).to(dev)
+    W = (torch.randn(NOUT, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(NOUT, generator=g).to(dev) if bias else None
+    res = torch.randn(R, NOUT, generator=g).to(dev) if residual else None
+    sc = (torch.rand(NOUT, generator=g) + 0.5).to(dev) if bn else None
+    sh = torch.randn(NOUT, generator=g).to(dev) if bn else None
+    Y = torch.empty(R, NOUT, device=dev)
+    vrpx.check(vrpx.lib().vrpx_debug_gemm(vrpx.ptr(X), R, K, vrpx.ptr(W), NOUT, vrpx.ptr(b), int(relu), vrpx.ptr(res),
+                                          vrpx.ptr(sc), vrpx.ptr(sh), vrpx.ptr(Y), path, vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    ref = X.double() @ W.double().T
+    if bias:
+        ref = ref + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    if residual:
+        ref = ref + res.double()
+    if bn:
+        ref = ref * sc.double() + sh.double()
+    return Y.double(), ref
+
+
+SHAPES = [(128, 128, 128), (1000, 128, 384), (777, 128, 512), (1300, 512, 128), (5, 128, 128)]
+
+
+@pytest.mark.parametrize("path", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("R,K,NOUT", SHAPES)
+def test_gemm_plain(path, R, K, NOUT):
+    Y, ref = _run(path, R, K, NOUT, False, False, False, False)
+    err = (Y - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # fp32-level accuracy is required of BOTH paths: 3xTF32 must stay within a few fp32 ulps of the SIMT result
+    assert err <= 2e-6 * max(scale, 1.0) * (K / 128) ** 0.5 + 1e-6, (path, R, K, NOUT, err, scale)
+
+
+@pytest.mark.parametrize("path", [1, 0], ids=["simt", "tcgen05"])
+def test_gemm_epilogues(path):
+    for (bias, relu, residual, bn) in [(True, False, False, False), (True, True, False, False),
+                                       (True, False, True, True), (False, False, True, False)]:
+        Y, ref = _run(path, 515, 128, 128, bias, relu, residual, bn, seed=3)
+        err = (Y - ref).abs().max().item()
+        assert err <= 1e-5, (path, bias, relu, residual, bn, err)
+
+
+def test_gemm_tc_in_place_residual():
+    """The encoder runs out-proj / FF2 with Y aliasing the residual (h <- BN(h + X W^T))."""
+    import vrpx
+
+    dev = vrpx.require_device()
+    R, K, NOUT = 900, 512, 128
+    X = torch.randn(R, K, device=dev)
+    W = torch.randn(NOUT, K, device=dev) / K ** 0.5
+    h = torch.randn(R, NOUT, device=dev)
+    ref = h.double() + X.double() @ W.double().T
+    vrpx.check(vrpx.lib().vrpx_debug_gemm(vrpx.ptr(X), R, K, vrpx.ptr(W), NOUT, None, 0, vrpx.ptr(h), None, None,
+                                          vrpx.ptr(h), 0, vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert (h.double() - ref).abs().max().item() <= 1e-5
