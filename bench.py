@@ -195,11 +195,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         out = one_step()
     T = out["steps"]
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     launches0 = vrpx.launch_count()
     per_step_events = [[ev(), ev(), ev()] for _ in range(a.steps)]
     e0, e1 = ev(), ev()

@@ -115,7 +115,6 @@ def test_large_random_walk_vs_oracle(kind):
     assert xy.min() >= 0 and xy.max() < 1 and depot.min() >= 0 and depot.max() < N
     if kind == "irp":
         C = 0.2449 * N + 26.12
-        nz = demand[np.arange(B)[:, None] != -1]
         assert demand[np.arange(B), depot].max() == 0 and demand.max() < 10 / C
     orc = EnvOracle(kind, xy, depot, demand)
     st_o = orc.get_state()

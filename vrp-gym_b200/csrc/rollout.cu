@@ -24,7 +24,9 @@ constexpr int NT = 256;       // threads per CTA
 constexpr int QW = NH * E;    // 1024: per-instance width of q~ / c
 constexpr size_t SMEM_X = (size_t)TM * E * sizeof(float);    // 16 KiB
 constexpr size_t SMEM_QC = (size_t)TM * QW * sizeof(float);  // 128 KiB
-constexpr size_t SMEM_TOTAL = SMEM_X + SMEM_QC;
+constexpr int WCHUNK_FLOATS = 16 * 512;                      // one staged weight chunk: 32 KiB
+constexpr size_t SMEM_W = 2 * (size_t)WCHUNK_FLOATS * sizeof(float);  // double buffer, 64 KiB
+constexpr size_t SMEM_TOTAL = SMEM_X + SMEM_QC + SMEM_W;
 
 struct RolloutParams {
   vrpx_env env;
@@ -90,34 +92,67 @@ __device__ __forceinline__ float reduce8(const float v[8], int lane) {
   return x;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------- GEMM-A: [TM x 128] · [128 x 1024]
-// Xs smem [TM][128]; Wt global [128][1024].  256 threads = 4 row groups x 64 column threads; each thread
-// 8 rows x 8 columns per half (columns half*512 + tx + 64 j).
+// Xs smem [TM][128]; Wt global [128][1024], streamed through a double-buffered smem stage with cp.async in
+// chunks of 16 k-rows x 512 columns (32 KiB).  256 threads = 4 row groups x 64 column threads; each thread owns
+// 8 rows x 8 columns of the current 512-column half: columns {4tx..4tx+3} and {256+4tx..+3} (conflict-free LDS.128).
 // EPI 0: qg[b][c] = acc + a_c[c]               (prologue: graph-embedding term + bias)
 // EPI 1: qg[b][c] += acc                       (step 1: `first` term, graph_decoder.py:111-113)
 // EPI 2: QC[m][c] = acc + qg[b][c] + loadf[m] * a_load[c]
+__device__ __forceinline__ void stage_a_chunk(const float* __restrict__ Wt, int chunk, float* __restrict__ dst) {
+  const int half = chunk >> 3, k0 = (chunk & 7) * 16;
+  const float* src = Wt + (size_t)k0 * QW + half * 512;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
+    int r = idx >> 7, c4 = idx & 127;
+    cp_async16(dst + r * 512 + c4 * 4, src + (size_t)r * QW + c4 * 4);
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float* __restrict__ Wt,
-                                       float* __restrict__ QC, const RolloutParams& p, int64_t base, int cnt,
-                                       const float* __restrict__ loadf) {
+                                       float* __restrict__ QC, float* __restrict__ Wb, const RolloutParams& p,
+                                       int64_t base, int cnt, const float* __restrict__ loadf) {
   const int tid = threadIdx.x, ty = tid >> 6, tx = tid & 63;
-  for (int half = 0; half < 2; ++half) {
-    float acc[8][8];
+  stage_a_chunk(Wt, 0, Wb);
+  cp_async_commit();
+  float acc[8][8];
+  for (int chunk = 0; chunk < 16; ++chunk) {
+    const int half = chunk >> 3, k0 = (chunk & 7) * 16;
+    if ((chunk & 7) == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    const float* wp = Wt + half * 512 + tx;
-#pragma unroll 1
-    for (int k0 = 0; k0 < E; k0 += 4) {
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    }
+    if (chunk + 1 < 16) {
+      stage_a_chunk(Wt, chunk + 1, Wb + ((chunk + 1) & 1) * WCHUNK_FLOATS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* wb = Wb + (chunk & 1) * WCHUNK_FLOATS;
+#pragma unroll
+    for (int kq = 0; kq < 16; kq += 4) {
       float4 xv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty * 8 + i) * E + k0);
+      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty * 8 + i) * E + k0 + kq);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        float wv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wv[j] = __ldg(wp + (size_t)(k0 + kk) * QW + 64 * j);
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * 512 + tx * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(wb + (kq + kk) * 512 + 256 + tx * 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
@@ -126,22 +161,34 @@ __device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float
         }
       }
     }
+    __syncthreads();  // the stage may be refilled by the next iteration's cp.async
+    if ((chunk & 7) == 7) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m = ty * 8 + i;
-      if (m >= cnt) continue;
-      int64_t b = base + m;
+      for (int i = 0; i < 8; ++i) {
+        const int m = ty * 8 + i;
+        if (m >= cnt) continue;
+        const int64_t b = base + m;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int c = half * 512 + tx + 64 * j;
-        if (EPI == 0) {
-          p.qg[b * QW + c] = acc[i][j] + p.w.a_c[c];
-        } else if (EPI == 1) {
-          p.qg[b * QW + c] += acc[i][j];
-        } else {
-          float y = acc[i][j] + p.qg[b * QW + c];
-          if (p.env.kind == VRPX_IRP) y = fmaf(loadf[m], p.w.a_load[c], y);
-          QC[m * QW + c] = y;
+        for (int g = 0; g < 2; ++g) {
+          const int c = half * 512 + g * 256 + tx * 4;
+          float4 v = make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]);
+          float4* qgp = reinterpret_cast<float4*>(p.qg + b * QW + c);
+          if (EPI == 0) {
+            const float4 ac = *reinterpret_cast<const float4*>(p.w.a_c + c);
+            *qgp = make_float4(v.x + ac.x, v.y + ac.y, v.z + ac.z, v.w + ac.w);
+          } else if (EPI == 1) {
+            float4 q = *qgp;
+            *qgp = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
+          } else {
+            const float4 q = *qgp;
+            v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+            if (p.env.kind == VRPX_IRP) {
+              const float4 al = *reinterpret_cast<const float4*>(p.w.a_load + c);
+              const float lf = loadf[m];
+              v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
+            }
+            *reinterpret_cast<float4*>(QC + m * QW + c) = v;
+          }
         }
       }
     }
@@ -149,10 +196,21 @@ __device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float
 }
 
 // ---------------------------------------------------------------- GEMM-B: [TM x 1024] · [1024 x 128]
-// C smem [TM][1024]; Mt global [1024][128].  256 threads = 4 k-groups x 4 row groups x 16 column threads,
-// 8 rows x 8 columns each over a quarter of K; partial sums reduced through shared memory.
+// C smem [TM][1024]; Mt global [1024][128] staged with cp.async: chunk kc = rows {kg*256 + kc*16 + r} of the four
+// k-groups (4 x 16 rows x 128 columns = 32 KiB).  256 threads = 4 k-groups x 4 row groups x 16 column threads,
+// 8 rows x 8 columns each ({4tx..+3} and {64+4tx..+3}) over a quarter of K; partial sums reduced through smem.
 // Result q^[m][e] (+ m_c) is written to Xs[TM][128].
-__device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict__ Xs,
+__device__ __forceinline__ void stage_b_chunk(const float* __restrict__ Mt, int kc, float* __restrict__ dst) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
+    int row = idx >> 5, c4 = idx & 31;    // row in [0,64): kg = row >> 4, r = row & 15
+    int k = (row >> 4) * 256 + kc * 16 + (row & 15);
+    cp_async16(dst + row * E + c4 * 4, Mt + (size_t)k * E + c4 * 4);
+  }
+}
+
+__device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict__ Xs, float* __restrict__ Wb,
                                        const RolloutParams& p) {
   const int tid = threadIdx.x, kg = tid >> 6, ty = (tid >> 4) & 3, tx = tid & 15;
   float acc[8][8];
@@ -160,31 +218,46 @@ __device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const float* wp = p.w.m_t + tx;
-#pragma unroll 1
-  for (int k0 = kg * 256; k0 < kg * 256 + 256; k0 += 4) {
-    float4 xv[8];
+  stage_b_chunk(p.w.m_t, 0, Wb);
+  cp_async_commit();
+  for (int kc = 0; kc < 16; ++kc) {
+    if (kc + 1 < 16) {
+      stage_b_chunk(p.w.m_t, kc + 1, Wb + ((kc + 1) & 1) * WCHUNK_FLOATS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* wb = Wb + (kc & 1) * WCHUNK_FLOATS + kg * 16 * E;
+    const int k0 = kg * 256 + kc * 16;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(QC + (ty * 8 + i) * QW + k0);
+    for (int kq = 0; kq < 16; kq += 4) {
+      float4 xv[8];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      float wv[8];
+      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(QC + (ty * 8 + i) * QW + k0 + kq);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wv[j] = __ldg(wp + (size_t)(k0 + kk) * E + 16 * j);
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * E + tx * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(wb + (kq + kk) * E + 64 + tx * 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
+        for (int i = 0; i < 8; ++i) {
+          float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+        }
       }
     }
+    __syncthreads();  // also orders the last reads of C before the partials overwrite it
   }
-  __syncthreads();  // every thread is done reading C before the partials overwrite it
   float* part = QC;  // [4][TM][128]
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) part[(kg * TM + ty * 8 + i) * E + tx + 16 * j] = acc[i][j];
+    for (int g = 0; g < 2; ++g)
+      *reinterpret_cast<float4*>(part + (kg * TM + ty * 8 + i) * E + g * 64 + tx * 4) =
+          make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]);
   __syncthreads();
   for (int o = tid; o < TM * E; o += NT) {
     float s = part[o] + part[TM * E + o] + part[2 * TM * E + o] + part[3 * TM * E + o];
@@ -205,6 +278,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Xs = reinterpret_cast<float*>(smem_raw);
   float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X);
+  float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X + SMEM_QC);
   __shared__ float s_loadf[TM];
   __shared__ int s_anyleft;
 
@@ -233,7 +307,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       *reinterpret_cast<float4*>(Xs + m * E + lane * 4) = g;
     }
     __syncthreads();
-    gemm_a<0>(Xs, p.w.ag_t, QC, p, base, cnt, s_loadf);
+    gemm_a<0>(Xs, p.w.ag_t, QC, Wb, p, base, cnt, s_loadf);
     __syncthreads();
   }
 
@@ -266,10 +340,10 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         }
       } else {
         if (t == 1 && kind != VRPX_IRP) {
-          gemm_a<1>(Xs, p.w.af_t, QC, p, base, cnt, s_loadf);
+          gemm_a<1>(Xs, p.w.af_t, QC, Wb, p, base, cnt, s_loadf);
           __syncthreads();  // qg updates are re-read by other threads' epilogue below? (same thread) — keep ordering explicit
         }
-        gemm_a<2>(Xs, p.w.al_t, QC, p, base, cnt, s_loadf);
+        gemm_a<2>(Xs, p.w.al_t, QC, Wb, p, base, cnt, s_loadf);
       }
       __syncthreads();
 
@@ -288,16 +362,34 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) nb[i] = __ldcg(nbm + i);
         const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
-        // pass 1: scores[hh][n]
-#pragma unroll 2
-        for (int n = 0; n < N; ++n) {
-          float4 hv = __ldg(hp + n * (E / 4));
-          float v[NH];
+        // pass 1: scores[hh][n]; rows are fetched four at a time, one batch ahead of their use
+        {
+          float4 nxt[4];
 #pragma unroll
-          for (int hh = 0; hh < NH; ++hh)
-            v[hh] = fmaf(qt[hh].x, hv.x, fmaf(qt[hh].y, hv.y, fmaf(qt[hh].z, hv.z, qt[hh].w * hv.w)));
-          float s = reduce8(v, lane);
-          if ((lane & 3) == 0) slot[myh * E + n] = s + (float)((nb[n >> 5] >> (n & 31)) & 1u);
+          for (int i = 0; i < 4; ++i) nxt[i] = (i < N) ? __ldg(hp + i * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int n0 = 0; n0 < N; n0 += 4) {
+            float4 hv4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hv4[i] = nxt[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = n0 + 4 + i;
+              if (n < N) nxt[i] = __ldg(hp + n * (E / 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = n0 + i;
+              if (n < N) {
+                const float4 hv = hv4[i];
+                float v[NH];
+#pragma unroll
+                for (int hh = 0; hh < NH; ++hh)
+                  v[hh] = fmaf(qt[hh].x, hv.x, fmaf(qt[hh].y, hv.y, fmaf(qt[hh].z, hv.z, qt[hh].w * hv.w)));
+                float sc = reduce8(v, lane);
+                if ((lane & 3) == 0) slot[myh * E + n] = sc + (float)((nb[n >> 5] >> (n & 31)) & 1u);
+              }
+            }
+          }
         }
         __syncwarp();
         // softmax per head over nodes (lane = node, 4 strides cover N <= 128)
@@ -339,18 +431,36 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         float4 c[NH];
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) c[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-        for (int n = 0; n < N; ++n) {
-          float4 hv = __ldg(hp + n * (E / 4));
-          float4 p0 = *reinterpret_cast<const float4*>(slot + n * 8);
-          float4 p1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
-          float pv[NH] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        {
+          float4 nxt[4];
 #pragma unroll
-          for (int hh = 0; hh < NH; ++hh) {
-            c[hh].x = fmaf(pv[hh], hv.x, c[hh].x);
-            c[hh].y = fmaf(pv[hh], hv.y, c[hh].y);
-            c[hh].z = fmaf(pv[hh], hv.z, c[hh].z);
-            c[hh].w = fmaf(pv[hh], hv.w, c[hh].w);
+          for (int i = 0; i < 4; ++i) nxt[i] = (i < N) ? __ldg(hp + i * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int n0 = 0; n0 < N; n0 += 4) {
+            float4 hv4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hv4[i] = nxt[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = n0 + 4 + i;
+              if (n < N) nxt[i] = __ldg(hp + n * (E / 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = n0 + i;
+              if (n < N) {
+                const float4 hv = hv4[i];
+                const float4 p0 = *reinterpret_cast<const float4*>(slot + n * 8);
+                const float4 p1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
+                const float pv[NH] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+                for (int hh = 0; hh < NH; ++hh) {
+                  c[hh].x = fmaf(pv[hh], hv.x, c[hh].x);
+                  c[hh].y = fmaf(pv[hh], hv.y, c[hh].y);
+                  c[hh].z = fmaf(pv[hh], hv.z, c[hh].z);
+                  c[hh].w = fmaf(pv[hh], hv.w, c[hh].w);
+                }
+              }
+            }
           }
         }
         __syncwarp();
@@ -362,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       __syncthreads();
 
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
-      gemm_b(QC, Xs, p);
+      gemm_b(QC, Xs, Wb, p);
 
       // ---------------- P4: logits, action, environment transition
       bool unfinished = false;
