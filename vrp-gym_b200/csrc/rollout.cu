@@ -20,7 +20,7 @@
 namespace vrpx {
 
 constexpr int TM = 32;        // instances per tile
-constexpr int NT = 256;       // threads per CTA
+constexpr int NT = 512;       // threads per CTA (16 warps; <= 128 registers per thread)
 constexpr int QW = NH * E;    // 1024: per-instance width of q~ / c
 constexpr size_t SMEM_X = (size_t)TM * E * sizeof(float);    // 16 KiB
 constexpr size_t SMEM_QC = (size_t)TM * QW * sizeof(float);  // 128 KiB
@@ -102,8 +102,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ---------------------------------------------------------------- GEMM-A: [TM x 128] · [128 x 1024]
 // Xs smem [TM][128]; Wt global [128][1024], streamed through a double-buffered smem stage with cp.async in
-// chunks of 16 k-rows x 512 columns (32 KiB).  256 threads = 4 row groups x 64 column threads; each thread owns
-// 8 rows x 8 columns of the current 512-column half: columns {4tx..4tx+3} and {256+4tx..+3} (conflict-free LDS.128).
+// chunks of 16 k-rows x 512 columns (32 KiB).  512 threads = 4 row groups x 128 column threads; each thread owns
+// 8 rows x 4 columns {4tx..4tx+3} of the current 512-column half (conflict-free LDS.128).
 // EPI 0: qg[b][c] = acc + a_c[c]               (prologue: graph-embedding term + bias)
 // EPI 1: qg[b][c] += acc                       (step 1: `first` term, graph_decoder.py:111-113)
 // EPI 2: QC[m][c] = acc + qg[b][c] + loadf[m] * a_load[c]
@@ -111,7 +111,7 @@ __device__ __forceinline__ void stage_a_chunk(const float* __restrict__ Wt, int 
   const int half = chunk >> 3, k0 = (chunk & 7) * 16;
   const float* src = Wt + (size_t)k0 * QW + half * 512;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 2048 / NT; ++i) {
     int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
     int r = idx >> 7, c4 = idx & 127;
     cp_async16(dst + r * 512 + c4 * 4, src + (size_t)r * QW + c4 * 4);
@@ -122,17 +122,17 @@ template <int EPI>
 __device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float* __restrict__ Wt,
                                        float* __restrict__ QC, float* __restrict__ Wb, const RolloutParams& p,
                                        int64_t base, int cnt, const float* __restrict__ loadf) {
-  const int tid = threadIdx.x, ty = tid >> 6, tx = tid & 63;
+  const int tid = threadIdx.x, ty = tid >> 7, tx = tid & 127;
   stage_a_chunk(Wt, 0, Wb);
   cp_async_commit();
-  float acc[8][8];
+  float acc[8][4];
   for (int chunk = 0; chunk < 16; ++chunk) {
     const int half = chunk >> 3, k0 = (chunk & 7) * 16;
     if ((chunk & 7) == 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     }
     if (chunk + 1 < 16) {
       stage_a_chunk(Wt, chunk + 1, Wb + ((chunk + 1) & 1) * WCHUNK_FLOATS);
@@ -142,7 +142,7 @@ __device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float
       cp_async_wait<0>();
     }
     __syncthreads();
-    const float* wb = Wb + (chunk & 1) * WCHUNK_FLOATS;
+    const float* wb = Wb + (chunk & 1) * WCHUNK_FLOATS + tx * 4;
 #pragma unroll
     for (int kq = 0; kq < 16; kq += 4) {
       float4 xv[8];
@@ -150,45 +150,42 @@ __device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float
       for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty * 8 + i) * E + k0 + kq);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * 512 + tx * 4);
-        const float4 w1 = *reinterpret_cast<const float4*>(wb + (kq + kk) * 512 + 256 + tx * 4);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * 512);
+        const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
         }
       }
     }
     __syncthreads();  // the stage may be refilled by the next iteration's cp.async
     if ((chunk & 7) == 7) {
+      const int c = half * 512 + tx * 4;
+      float4 ac = make_float4(0.f, 0.f, 0.f, 0.f), al = ac;
+      if (EPI == 0) ac = *reinterpret_cast<const float4*>(p.w.a_c + c);
+      if (EPI == 2 && p.env.kind == VRPX_IRP) al = *reinterpret_cast<const float4*>(p.w.a_load + c);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = ty * 8 + i;
         if (m >= cnt) continue;
         const int64_t b = base + m;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int c = half * 512 + g * 256 + tx * 4;
-          float4 v = make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]);
-          float4* qgp = reinterpret_cast<float4*>(p.qg + b * QW + c);
-          if (EPI == 0) {
-            const float4 ac = *reinterpret_cast<const float4*>(p.w.a_c + c);
-            *qgp = make_float4(v.x + ac.x, v.y + ac.y, v.z + ac.z, v.w + ac.w);
-          } else if (EPI == 1) {
-            float4 q = *qgp;
-            *qgp = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
-          } else {
-            const float4 q = *qgp;
-            v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
-            if (p.env.kind == VRPX_IRP) {
-              const float4 al = *reinterpret_cast<const float4*>(p.w.a_load + c);
-              const float lf = loadf[m];
-              v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
-            }
-            *reinterpret_cast<float4*>(QC + m * QW + c) = v;
+        float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        float4* qgp = reinterpret_cast<float4*>(p.qg + b * QW + c);
+        if (EPI == 0) {
+          *qgp = make_float4(v.x + ac.x, v.y + ac.y, v.z + ac.z, v.w + ac.w);
+        } else if (EPI == 1) {
+          float4 q = *qgp;
+          *qgp = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
+        } else {
+          const float4 q = *qgp;
+          v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+          if (p.env.kind == VRPX_IRP) {
+            const float lf = loadf[m];
+            v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
           }
+          *reinterpret_cast<float4*>(QC + m * QW + c) = v;
         }
       }
     }
@@ -197,12 +194,12 @@ __device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float
 
 // ---------------------------------------------------------------- GEMM-B: [TM x 1024] · [1024 x 128]
 // C smem [TM][1024]; Mt global [1024][128] staged with cp.async: chunk kc = rows {kg*256 + kc*16 + r} of the four
-// k-groups (4 x 16 rows x 128 columns = 32 KiB).  256 threads = 4 k-groups x 4 row groups x 16 column threads,
-// 8 rows x 8 columns each ({4tx..+3} and {64+4tx..+3}) over a quarter of K; partial sums reduced through smem.
+// k-groups (4 x 16 rows x 128 columns = 32 KiB).  512 threads = 4 k-groups x 4 row groups x 32 column threads,
+// 8 rows x 4 columns {4tx..+3} each over a quarter of K; partial sums reduced through smem.
 // Result q^[m][e] (+ m_c) is written to Xs[TM][128].
 __device__ __forceinline__ void stage_b_chunk(const float* __restrict__ Mt, int kc, float* __restrict__ dst) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 2048 / NT; ++i) {
     int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
     int row = idx >> 5, c4 = idx & 31;    // row in [0,64): kg = row >> 4, r = row & 15
     int k = (row >> 4) * 256 + kc * 16 + (row & 15);
@@ -212,12 +209,12 @@ __device__ __forceinline__ void stage_b_chunk(const float* __restrict__ Mt, int 
 
 __device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict__ Xs, float* __restrict__ Wb,
                                        const RolloutParams& p) {
-  const int tid = threadIdx.x, kg = tid >> 6, ty = (tid >> 4) & 3, tx = tid & 15;
-  float acc[8][8];
+  const int tid = threadIdx.x, kg = tid >> 7, ty = (tid >> 5) & 3, tx = tid & 31;
+  float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   stage_b_chunk(p.w.m_t, 0, Wb);
   cp_async_commit();
   for (int kc = 0; kc < 16; ++kc) {
@@ -229,7 +226,7 @@ __device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict
       cp_async_wait<0>();
     }
     __syncthreads();
-    const float* wb = Wb + (kc & 1) * WCHUNK_FLOATS + kg * 16 * E;
+    const float* wb = Wb + (kc & 1) * WCHUNK_FLOATS + kg * 16 * E + tx * 4;
     const int k0 = kg * 256 + kc * 16;
 #pragma unroll
     for (int kq = 0; kq < 16; kq += 4) {
@@ -238,14 +235,13 @@ __device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict
       for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(QC + (ty * 8 + i) * QW + k0 + kq);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * E + tx * 4);
-        const float4 w1 = *reinterpret_cast<const float4*>(wb + (kq + kk) * E + 64 + tx * 4);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * E);
+        const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
         }
       }
     }
@@ -254,10 +250,8 @@ __device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict
   float* part = QC;  // [4][TM][128]
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int g = 0; g < 2; ++g)
-      *reinterpret_cast<float4*>(part + (kg * TM + ty * 8 + i) * E + g * 64 + tx * 4) =
-          make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]);
+    *reinterpret_cast<float4*>(part + (kg * TM + ty * 8 + i) * E + tx * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   __syncthreads();
   for (int o = tid; o < TM * E; o += NT) {
     float s = part[o] + part[TM * E + o] + part[2 * TM * E + o] + part[3 * TM * E + o];
@@ -481,17 +475,26 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         float* slot = QC + m * QW;  // free scratch again
         const float4 qh = *reinterpret_cast<const float4*>(Xs + m * E + lane * 4);
         const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
-        for (int n0 = 0; n0 < N; n0 += 8) {
-          float v[8];
+        {
+          float4 nxt[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            int n = n0 + i;
-            float4 hv = (n < N) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[i] = fmaf(qh.x, hv.x, fmaf(qh.y, hv.y, fmaf(qh.z, hv.z, qh.w * hv.w)));
+          for (int i = 0; i < 8; ++i) nxt[i] = (i < N) ? __ldg(hp + i * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int n0 = 0; n0 < N; n0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 hv = nxt[i];
+              v[i] = fmaf(qh.x, hv.x, fmaf(qh.y, hv.y, fmaf(qh.z, hv.z, qh.w * hv.w)));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int n = n0 + 8 + i;
+              nxt[i] = (n < N) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float sc = reduce8(v, lane);
+            int n = n0 + ((lane >> 2) & 7);
+            if ((lane & 3) == 0 && n < N) slot[n] = 10.0f * tanhf(sc);
           }
-          float s = reduce8(v, lane);
-          int n = n0 + ((lane >> 2) & 7);
-          if ((lane & 3) == 0 && n < N) slot[n] = 10.0f * tanhf(s);
         }
         __syncwarp();
         // own mask (graph_decoder.py:98), 4 consecutive nodes per lane
