@@ -123,10 +123,44 @@ VRPX_API int64_t vrpx_encoder_workspace_bytes(int64_t B, int32_t N);
  *   train  0: running statistics; 1: batch statistics over all B*N rows + running-stat update
  *          (momentum 0.1, unbiased variance), graph_encoder.py:150-154;
  *   h      [B][N][128] f32 output embeddings;
- *   gemm_path 0: tcgen05 3xTF32 tensor-core GEMMs; 1: fp32 SIMT GEMMs (debug / cross-check). */
+ *   gemm_path 0: tcgen05 3xTF32 tensor-core GEMMs; 1: fp32 SIMT GEMMs (debug / cross-check);
+ *   saved  NULL, or (train mode) a buffer of vrpx_encoder_saved_bytes() that receives the activations the
+ *          backward pass needs. */
 VRPX_API int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, const float* x,
                          const int32_t* depot, int64_t B, int32_t N, int32_t train, float* h, void* ws,
-                         int64_t ws_bytes, int32_t gemm_path, void* stream);
+                         int64_t ws_bytes, int32_t gemm_path, float* saved, void* stream);
+
+/* Bytes of the activation buffer `saved` (train mode only; pass NULL when no backward will follow). */
+VRPX_API int64_t vrpx_encoder_saved_bytes(int64_t B, int32_t N);
+
+/* Transposed copies of the dense encoder weights (dX = dY · W runs as a forward GEMM on W^T). */
+typedef struct vrpx_encoder_layer_t {
+  const float* in_proj_wT;  /* [128][384] */
+  const float* out_proj_wT; /* [128][128] */
+  const float* ff0_wT;      /* [128][512] */
+  const float* ff2_wT;      /* [512][128] */
+} vrpx_encoder_layer_t;
+typedef struct vrpx_encoder_weights_t {
+  vrpx_encoder_layer_t layer[VRPX_LAYERS];
+} vrpx_encoder_weights_t;
+
+/* Gradient buffers, same shapes as the parameters, ACCUMULATED into (+=). */
+typedef struct vrpx_encoder_layer_grads {
+  float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *bn1_w, *bn1_b, *ff0_w, *ff0_b, *ff2_w, *ff2_b, *bn2_w, *bn2_b;
+} vrpx_encoder_layer_grads;
+typedef struct vrpx_encoder_grads {
+  float *node_w, *node_b, *depot_w, *depot_b; /* depot_* may be NULL (TSP) */
+  vrpx_encoder_layer_grads layer[VRPX_LAYERS];
+} vrpx_encoder_grads;
+
+VRPX_API int64_t vrpx_encoder_backward_workspace_bytes(int64_t B, int32_t N);
+
+/* Backward of the train-mode encoder forward (BatchNorm with batch statistics).  `saved` is the buffer the forward
+ * filled; `g` [B][N][128] holds dL/dh on entry and is overwritten (it ends as dL/d(embedding)). */
+VRPX_API int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_encoder_weights_t* wt, const vrpx_env* env,
+                                   const float* x, const int32_t* depot, int64_t B, int32_t N, const float* saved,
+                                   float* g, const vrpx_encoder_grads* grads, void* ws, int64_t ws_bytes,
+                                   int32_t gemm_path, void* stream);
 
 /* Decoder parameters after host-side packing (agents/graph_decoder.py:29-44); vrpx/packing.py derives
  * each array from the state_dict (in float64, rounded once to f32).  With W_q/W_k/W_v/b_* the in-projections of
@@ -145,6 +179,13 @@ typedef struct vrpx_decoder_weights {
   const float *ag_t, *af_t, *al_t, *a_c, *a_q0, *a_load;
   const float *m_t, *m_c;
 } vrpx_decoder_weights;
+
+/* Optional per-step history written by vrpx_rollout for the recompute-based backward (any field may be NULL). */
+typedef struct vrpx_rollout_trace {
+  uint32_t* mask_hist; /* [Tmax][B][4] decoder-visible mask bits BEFORE each step */
+  float* load_hist;    /* [Tmax][B] f32 vehicle load before each step (IRP) */
+  float* qg0;          /* [B][1024] per-episode query table before the `first` fold */
+} vrpx_rollout_trace;
 
 typedef enum vrpx_rollout_mode { VRPX_GREEDY = 0, VRPX_SAMPLE = 1, VRPX_TEACHER = 2 } vrpx_rollout_mode;
 
@@ -167,11 +208,48 @@ VRPX_API int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N);
  *   cost     [B] f32 = -(acc_loss): f32 accumulation of f32(reward) in step order (graph_tsp_agent.py:85)
  *   steps    [1] int32 number of steps executed (env.step_count)
  *   logits   optional [Tmax][B][N] f32 dump of the masked pointer logits (tests), or NULL
+ *   trace    optional history for vrpx_decoder_backward, or NULL
  *   seed/offset  Philox key / global instance-id offset (shard-invariant sampling)            */
 VRPX_API int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float* h, int32_t mode,
                  int64_t coupling, uint64_t seed, uint64_t offset, uint8_t* tape, int32_t t_begin, int32_t Tmax,
-                 float* logp, float* cost, int32_t* steps, float* logits, void* ws, int64_t ws_bytes,
-                 void* stream);
+                 float* logp, float* cost, int32_t* steps, float* logits, const vrpx_rollout_trace* trace,
+                 void* ws, int64_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- REINFORCE backward (decoder part)
+ * loss = mean_b(advantage_b * sum_t log p(a_{b,t}))  (agents/graph_tsp_agent.py:179-186).  The backward is
+ * recompute-based: it replays every decode step from (h, tape, trace) and back-propagates wts[b] = dL/dlogp_b. */
+typedef struct vrpx_decoder_bwd_weights {
+  const float* m_n;  /* [128][1024]  = transpose of m_t   (dc  = dq^ · M)   */
+  const float* al_n; /* [1024][128]  = transpose of al_t  (dx_l = dq~ · A_l) */
+} vrpx_decoder_bwd_weights;
+
+typedef struct vrpx_decoder_grads {
+  float* dH;     /* [B][N][128] accumulated (caller zero-fills): dL/dh from scores, glimpse values, logits, h[last] */
+  float* D0;     /* [B][1024] dq~ of step 0            (caller zero-fills) */
+  float* D1;     /* [B][1024] sum over steps >= 1 of dq~ (caller zero-fills) */
+  float* Dl;     /* [B][1024] IRP: sum_t load_t dq~_t  (caller zero-fills; NULL for TSP/VRP) */
+  float* d_al_t; /* [128][1024] accumulated */
+  float* d_m_t;  /* [1024][128] accumulated */
+  float* d_m_c;  /* [128] accumulated */
+} vrpx_decoder_grads;
+
+VRPX_API int64_t vrpx_decoder_backward_workspace_bytes(int64_t B, int32_t N);
+
+/* Backward of vrpx_rollout for one episode.  `trace` and `qg` (the rollout workspace's Q~g table = ws + 4096 bytes)
+ * come from the forward call that produced `tape`; T = number of executed steps; wts [B] f32. */
+VRPX_API int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, const vrpx_decoder_bwd_weights* wb,
+                                   const float* h, const uint8_t* tape, int32_t T, int64_t coupling,
+                                   const vrpx_rollout_trace* trace, const float* qg, const float* wts,
+                                   const vrpx_decoder_grads* g, void* ws, int64_t ws_bytes, void* stream);
+
+/* Small per-episode helpers used by the backward passes (decoder epilogue, encoder weight gradients):
+ *   C[M][N] += A^T · Bm  with A [R][M], Bm [R][N] (reduction over rows, red.add);  out[c] += sum_r X[r][c];
+ *   G[b] = mean_n h[b,n], Xf[b] = h[b, tape0[b]];  dH[b,n] += dG[b]/N, dH[b,tape0[b]] += dXf[b]. */
+VRPX_API int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R, int32_t M, int32_t N, void* stream);
+VRPX_API int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out, void* stream);
+VRPX_API int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B, int32_t N, float* G, float* Xf, void* stream);
+VRPX_API int vrpx_episode_scatter(float* dH, const uint8_t* tape0, int64_t B, int32_t N, const float* dG, const float* dXf,
+                                  void* stream);
 
 /* Test hook (tests/test_gemm.py): Y[R][NOUT] = epilogue(X[R][K] · W[NOUT][K]^T) through the tcgen05 3xTF32
  * path (path 0) or the fp32 SIMT path (path 1); epilogue = +bias, ReLU, +residual, *scale+shift (each optional). */

@@ -47,7 +47,7 @@ class GraphDecoder(nn.Module):
         return self._packed[irp].get(self, irp, device)
 
     def rollout_episode(self, env, h: torch.Tensor, *, greedy: bool, tape_in=None, want_logits: bool = False,
-                        coupling=None, seed: int = 0, offset: int = 0):
+                        coupling=None, seed: int = 0, offset: int = 0, save_for_backward: bool = False):
         """Run every decode step + environment transition of one episode in one persistent launch.
 
         env: device-resident TSPEnv/VRPEnv/IRPEnv in its reset state.  h: (B,N,128) f32 CUDA embeddings.
@@ -72,15 +72,26 @@ class GraphDecoder(nn.Module):
         nbytes = int(L.vrpx_rollout_workspace_bytes(B, N))
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         G = B if coupling is None else int(coupling)
+        trace, saved = None, None
+        if save_for_backward:
+            saved = {"mask_hist": torch.empty((Tmax, B, 4), dtype=torch.int32, device=dev),
+                     "load_hist": torch.empty((Tmax, B), dtype=torch.float32, device=dev),
+                     "qg0": torch.empty((B, 1024), dtype=torch.float32, device=dev)}
+            trace = vrpx.RolloutTrace(saved["mask_hist"].data_ptr(), saved["load_hist"].data_ptr(), saved["qg0"].data_ptr())
         env._sync_instances()
         vrpx.check(L.vrpx_rollout(C.byref(env._view()), C.byref(w), vrpx.ptr(h), mode, G, C.c_uint64(seed),
                                   C.c_uint64(offset), vrpx.ptr(tape), 0, Tmax, vrpx.ptr(logp), vrpx.ptr(cost),
                                   vrpx.ptr(steps), vrpx.ptr(logits) if logits is not None else None,
+                                  C.byref(trace) if trace is not None else None,
                                   vrpx.ptr(ws), nbytes, vrpx.stream_ptr(dev)))
         T = int(steps.item())
         env.step_count += T
         env._host_cur = None
-        out = {"cost": cost, "logp": logp, "steps": T, "tape": tape[:T]}
+        out = {"cost": cost, "logp": logp, "steps": T, "tape": tape[:T], "coupling": G}
+        if saved is not None:
+            saved["qg"] = ws[4096:].view(torch.float32).view(B, 1024)  # Q~g incl. the `first` fold (kRolloutSmall = 4096)
+            saved["ws"] = ws
+            out["saved"] = saved
         if logits is not None:
             out["logits"] = logits[:T]
         return out
@@ -126,7 +137,7 @@ class GraphDecoder(nn.Module):
         prev_logp = ep["logp"].clone()
         vrpx.check(L.vrpx_rollout(C.byref(v), C.byref(w), vrpx.ptr(ep["h"]), vrpx.GREEDY if rollout else vrpx.SAMPLE,
                                   B, C.c_uint64(seed), C.c_uint64(0), vrpx.ptr(ep["tape"]), ep["t"], 1,
-                                  vrpx.ptr(ep["logp"]), vrpx.ptr(ep["cost"]), vrpx.ptr(ep["steps"]), None,
+                                  vrpx.ptr(ep["logp"]), vrpx.ptr(ep["cost"]), vrpx.ptr(ep["steps"]), None, None,
                                   vrpx.ptr(ep["ws"]), ep["ws_bytes"], st))
         nn_idx = ep["tape"][0].to(torch.long)
         ep["cur"].copy_(nn_idx.to(torch.int32))

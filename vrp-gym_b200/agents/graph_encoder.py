@@ -38,9 +38,10 @@ class MultiHeadAttentionLayer(nn.Module):
         self.ff = nn.Sequential(nn.Linear(embedding_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, embedding_dim))
 
 
-def run_encoder(enc: "GraphEncoder", *, env=None, x=None, depot=None, gemm_path: int = 0) -> torch.Tensor:
+def run_encoder(enc: "GraphEncoder", *, env=None, x=None, depot=None, gemm_path: int = 0, save: bool = False):
     """Launch vrpx_encoder_forward.  Features come from a device-resident env or from x (B,N,f) f32 CUDA;
-    depot (B,) int32 CUDA or None.  Returns h (B,N,128) f32 on the device."""
+    depot (B,) int32 CUDA or None.  Returns h (B,N,128) f32 on the device; with save=True (train mode only) returns
+    (h, saved) where `saved` holds the activations vrpx_encoder_backward needs."""
     dev = vrpx.require_device(env._device if env is not None else x.device)
     if next(enc.parameters()).device != dev:
         enc.to(dev)
@@ -56,16 +57,21 @@ def run_encoder(enc: "GraphEncoder", *, env=None, x=None, depot=None, gemm_path:
     if not train:  # eval mode is per-instance: cap the scratch and let the library chunk the batch
         need = min(need, max(int(L.vrpx_encoder_workspace_bytes(1, N)), 8 << 30))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    saved = None
+    if save:
+        assert train, "activations are only saved in train mode"
+        saved = torch.empty((int(L.vrpx_encoder_saved_bytes(B, N)) // 4,), dtype=torch.float32, device=dev)
     view = env._view() if env is not None else None
     vrpx.check(L.vrpx_encoder_forward(C.byref(w), C.byref(view) if view is not None else None,
                                       vrpx.ptr(x) if x is not None else None,
                                       vrpx.ptr(depot) if depot is not None else None,
-                                      B, N, train, vrpx.ptr(h), vrpx.ptr(ws), need, gemm_path, vrpx.stream_ptr(dev)))
+                                      B, N, train, vrpx.ptr(h), vrpx.ptr(ws), need, gemm_path,
+                                      vrpx.ptr(saved) if saved is not None else None, vrpx.stream_ptr(dev)))
     if train:
         for layer in enc.attention_layers:  # BatchNorm1d bookkeeping the kernel does not touch
             layer.bn1.norm.num_batches_tracked += 1
             layer.bn2.norm.num_batches_tracked += 1
-    return h
+    return (h, saved) if save else h
 
 
 class GraphEncoder(nn.Module):

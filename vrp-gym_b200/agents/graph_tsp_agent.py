@@ -43,6 +43,17 @@ class TSPModel(nn.Module):
         self.sample_offset = 0    # global id of this shard's first instance (shard-invariant sampling)
         self.last_rollout = None  # dict from GraphDecoder.rollout_episode (tape, steps, ...)
 
+    def backward(self, wts: torch.Tensor):
+        """Accumulate d(sum_b wts[b] * log_prob[b])/d(theta) of the LAST sampled train-mode rollout into .grad."""
+        from vrpx import backward as bw
+
+        ctx = self.last_rollout
+        if ctx is None or "enc_saved" not in ctx:
+            raise vrpx.VrpxError("no rollout recorded for backward: call model(env, rollout=False) in train mode with grad enabled")
+        dH = bw.decoder_backward(self.decoder, ctx["env"], ctx["emb"], ctx, wts, gemm_path=self.encoder.gemm_path)
+        bw.encoder_backward(self.encoder, ctx["env"], ctx["depot"], ctx["enc_saved"], dH, gemm_path=self.encoder.gemm_path)
+        self.last_rollout = None  # the saved activations are large: release them
+
     def forward(self, env, rollout: bool = False, *, tape=None, want_logits: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """Play the environment to the end.  rollout=True: greedy; False: sample (Philox stream keyed by the
         torch global seed).  Returns (acc_loss = -tour length (B,), acc_log_prob (B,)) on the device."""
@@ -52,11 +63,20 @@ class TSPModel(nn.Module):
         if next(self.parameters()).device != dev:
             self.to(dev)
         depot = env._depot if self._USES_DEPOT_EMBED else None
-        h = run_encoder(self.encoder, env=env, depot=depot, gemm_path=self.encoder.gemm_path)
+        # a sampled rollout of a model in train mode under grad is the REINFORCE forward: keep what backward needs
+        need_grad = self.training and torch.is_grad_enabled() and (not rollout)
+        enc_saved = None
+        if need_grad:
+            h, enc_saved = run_encoder(self.encoder, env=env, depot=depot, gemm_path=self.encoder.gemm_path, save=True)
+        else:
+            h = run_encoder(self.encoder, env=env, depot=depot, gemm_path=self.encoder.gemm_path)
         seed = 0 if (rollout or tape is not None) else int(torch.randint(0, 2 ** 62, (1,)).item())
         out = self.decoder.rollout_episode(env, h, greedy=rollout, tape_in=tape, want_logits=want_logits,
-                                           coupling=self.coupling, seed=seed, offset=self.sample_offset)
+                                           coupling=self.coupling, seed=seed, offset=self.sample_offset,
+                                           save_for_backward=need_grad)
         out["emb"] = h
+        if need_grad:
+            out["enc_saved"], out["env"], out["depot"] = enc_saved, env, depot
         self.last_rollout = out
         self.decoder.reset()
         return -out["cost"], out["logp"]
@@ -121,9 +141,13 @@ class TSPAgent:
 
     def policy_gradient_step(self, advantage, log_prob):
         """loss = mean(advantage * log_prob); backward; Adam step (reference :179-186)."""
-        raise vrpx.VrpxError(
-            "REINFORCE backward is not built yet in this round: the CUDA path covers rollouts (evaluate / step); "
-            "there is deliberately no torch-autograd fallback")
+        B = advantage.shape[0]
+        loss = (advantage * log_prob).mean()
+        self.opt.zero_grad()
+        # d loss / d log_prob_b = advantage_b / B; the gradient flows only through log_prob (advantage is data)
+        self.model.backward(advantage.detach() / B)
+        self.opt.step()
+        return loss
 
     def save_model(self, episode: int, check_point_dir: str) -> None:
         if not os.path.exists(check_point_dir):

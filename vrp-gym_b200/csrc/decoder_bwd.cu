@@ -1,0 +1,684 @@
+// decoder_bwd.cu — recompute-based backward of the fused decoder rollout (REINFORCE path,
+// agents/graph_tsp_agent.py:178-186: loss = mean(advantage * sum_t log p(a_t)); loss.backward()).
+//
+// Given the action tape, every decode step depends only on (h, tape, packed weights): step t reads
+// last = tape[t-1], first = tape[0], the recorded masks and loads.  So instead of storing (B,T,·) activations the
+// backward RECOMPUTES each step's forward (same tile GEMMs / per-instance phases as rollout.cu) and immediately
+// back-propagates d(logp_{b,t}) * w_b, accumulating
+//     dH            (B,N,128)   gradient w.r.t. the encoder output (all paths: scores, glimpse values, pointer
+//                               logits, h[last]; the graph-mean / h[first] terms are added by the epilogue)
+//     d_al_t, d_m_t, d_m_c      gradients of the packed per-step weights (red.global.add)
+//     D0, D1 (B,1024)           dq~ at step 0 / summed over steps >= 1  -> per-episode terms (A_g, A_f, a_c, a_q0)
+//     Dl (B,1024)               IRP: sum_t load_t * dq~_t -> a_load
+// Tiles are the outer loop and steps the inner loop, so a CTA owns its instances' dH rows for the whole episode
+// (plain read-modify-write, L2 resident) and no grid barrier is needed.
+//
+// Notation:  q~ = A_l x_l + Q~g (+ load a_load);  s_hn = q~_h·h_n + mask;  p = softmax_n(s);
+// c_h = sum_n p_hn h_n;  q^ = M c + m_c;  z_n = q^·h_n;  u_n = 10 tanh z_n;  pi = softmax(u | unmasked).
+#include "tile_gemm.cuh"
+
+namespace vrpx {
+
+struct DecBwdParams {
+  int kind, N, T;
+  long long B, G;
+  const float* h;
+  const uint8_t* tape;
+  const uint32_t* mask_hist;
+  const float* load_hist;
+  const float *qg0, *qg;
+  const float* wts;
+  const float *al_t, *a_q0, *a_load, *m_t, *m_c, *m_n, *al_n;
+  float *dH, *D0, *D1, *Dl, *d_al_t, *d_m_t, *d_m_c;
+  float* scratch;  // [grid][TM][3][1024]: q~ | p[n][8] | dz[128], q^[128]
+};
+
+constexpr size_t BWD_SMEM = SMEM_X + SMEM_QC + SMEM_W + SMEM_X;  // Xs | QC | Wb | DQ  = 224 KiB
+
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* Xs = reinterpret_cast<float*>(smem_raw);
+  float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X);
+  float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X + SMEM_QC);
+  float* DQ = reinterpret_cast<float*>(smem_raw + SMEM_X + SMEM_QC + SMEM_W);
+  __shared__ float s_loadf[TM], s_w[TM];
+  __shared__ int s_act[TM], s_prev[TM], s_live[TM], s_anylive;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, kind = p.kind;
+  const int64_t B = p.B;
+  const int64_t ntiles = (B + TM - 1) / TM;
+  const float* __restrict__ h = p.h;
+  float* SC = p.scratch + (size_t)blockIdx.x * TM * 3 * QW;
+  float* su = Wb + warp * 128;  // per-warp scratch for u (Wb is idle outside the GEMM phases)
+  float mc_acc = 0.f;           // d m_c[tid] for tid < 128, flushed once at the end
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TM;
+    const int cnt = (int)((B - base < TM) ? (B - base) : TM);
+    for (int t = 0; t < p.T; ++t) {
+      // ---------------- B0: per-instance step metadata, gather x_l = h[b, tape[t-1]]
+      if (tid == 0) s_anylive = 0;
+      __syncthreads();
+      for (int m = warp; m < TM; m += NT / 32) {
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        int prev = -1, act = 0, live = 0;
+        float w = 0.f, lf = 0.f;
+        if (m < cnt) {
+          const int64_t b = base + m;
+          act = (int)p.tape[(int64_t)t * B + b];
+          w = p.wts[b];
+          lf = p.load_hist ? p.load_hist[(int64_t)t * B + b] : 0.f;
+          if (t > 0) {
+            prev = (int)p.tape[(int64_t)(t - 1) * B + b];
+            xv = __ldg(reinterpret_cast<const float4*>(h + (b * N + prev) * E) + lane);
+          }
+          // an instance with a single feasible node has log p = 0 identically: no gradient
+          uint32_t mw = p.mask_hist[((int64_t)t * B + b) * 4 + (lane & 3)];
+          int free_cnt = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) free_cnt += __popc(~__shfl_sync(0xffffffffu, mw, i) & full_bits(N).w[i]);
+          live = (w != 0.f && free_cnt > 1) ? 1 : 0;
+        }
+        *reinterpret_cast<float4*>(Xs + m * E + lane * 4) = xv;
+        if (lane == 0) {
+          s_loadf[m] = lf; s_w[m] = w; s_act[m] = act; s_prev[m] = prev; s_live[m] = live;
+          if (live) s_anylive = 1;
+        }
+      }
+      __syncthreads();
+      const int anylive = s_anylive;
+      __syncthreads();           // everyone has read the flag before the next iteration may reset it
+      if (!anylive) continue;    // uniform: whole tile idle at this step
+
+      // ---------------- B1: q~ (recompute)
+      if (t == 0) {
+        for (int o = tid; o < cnt * QW; o += NT) {
+          int m = o >> 10, c = o & (QW - 1);
+          float y = p.qg0[(base + m) * QW + c] + p.a_q0[c];
+          if (kind == VRPX_IRP) y = fmaf(s_loadf[m], p.a_load[c], y);
+          QC[o] = y;
+        }
+      } else {
+        tile_gemm_wide(Xs, p.al_t, Wb, [&](int m, int c, float4 v) {
+          if (m >= cnt) return;
+          const float4 q = *reinterpret_cast<const float4*>(p.qg + (base + m) * QW + c);
+          v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+          if (kind == VRPX_IRP) {
+            const float4 al = *reinterpret_cast<const float4*>(p.a_load + c);
+            const float lf = s_loadf[m];
+            v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
+          }
+          *reinterpret_cast<float4*>(QC + m * QW + c) = v;
+        });
+      }
+      __syncthreads();
+
+      // ---------------- B2: glimpse forward (scores, p, c); q~ and p are parked in the per-CTA scratch
+      for (int m = warp; m < cnt; m += NT / 32) {
+        const int64_t b = base + m;
+        float* slot = QC + m * QW;
+        float* sc_q = SC + (size_t)m * 3 * QW;
+        float* sc_p = sc_q + QW;
+        float4 qt[NH];
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          qt[hh] = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
+          *reinterpret_cast<float4*>(sc_q + hh * E + lane * 4) = qt[hh];
+        }
+        __syncwarp();
+        const int myh = (lane >> 2) & 7;
+        const uint32_t* nbm = p.mask_hist + ((int64_t)t * B + quirk_row(b, myh, p.G)) * 4;
+        uint32_t nb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nb[i] = nbm[i];
+        const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
+        for (int n0 = 0; n0 < N; n0 += 4) {
+          float4 hv4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hv4[i] = (n0 + i < N) ? __ldg(hp + (n0 + i) * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = n0 + i;
+            if (n < N) {
+              const float4 hv = hv4[i];
+              float v[NH];
+#pragma unroll
+              for (int hh = 0; hh < NH; ++hh)
+                v[hh] = fmaf(qt[hh].x, hv.x, fmaf(qt[hh].y, hv.y, fmaf(qt[hh].z, hv.z, qt[hh].w * hv.w)));
+              float sc = reduce8(v, lane);
+              if ((lane & 3) == 0) slot[myh * E + n] = sc + (float)((nb[n >> 5] >> (n & 31)) & 1u);
+            }
+          }
+        }
+        __syncwarp();
+        float pr[NH][4];
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int n = lane + 32 * i;
+            pr[hh][i] = (n < N) ? slot[hh * E + n] : -INFINITY;
+            mx = fmaxf(mx, pr[hh][i]);
+          }
+          mx = warp_max(mx);
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int n = lane + 32 * i;
+            pr[hh][i] = (n < N) ? expf(pr[hh][i] - mx) : 0.f;
+            sum += pr[hh][i];
+          }
+          sum = warp_sum(sum);
+          float inv = 1.0f / sum;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pr[hh][i] *= inv;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int n = lane + 32 * i;
+          if (n < N) {
+            const float4 a0 = make_float4(pr[0][i], pr[1][i], pr[2][i], pr[3][i]);
+            const float4 a1 = make_float4(pr[4][i], pr[5][i], pr[6][i], pr[7][i]);
+            *reinterpret_cast<float4*>(slot + n * 8) = a0;
+            *reinterpret_cast<float4*>(slot + n * 8 + 4) = a1;
+            *reinterpret_cast<float4*>(sc_p + n * 8) = a0;
+            *reinterpret_cast<float4*>(sc_p + n * 8 + 4) = a1;
+          }
+        }
+        __syncwarp();
+        float4 c[NH];
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) c[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n = 0; n < N; ++n) {
+          const float4 hv = __ldg(hp + n * (E / 4));
+          const float4 p0 = *reinterpret_cast<const float4*>(slot + n * 8);
+          const float4 p1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
+          const float pv[NH] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) {
+            c[hh].x = fmaf(pv[hh], hv.x, c[hh].x);
+            c[hh].y = fmaf(pv[hh], hv.y, c[hh].y);
+            c[hh].z = fmaf(pv[hh], hv.z, c[hh].z);
+            c[hh].w = fmaf(pv[hh], hv.w, c[hh].w);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) *reinterpret_cast<float4*>(slot + hh * E + lane * 4) = c[hh];
+      }
+      for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[o] = 0.f;
+      __syncthreads();
+
+      // ---------------- B3: q^ = C · M^T + m_c -> DQ   (partials go through Wb: QC must keep c for the dM update)
+      tile_gemm_tall(QC, p.m_t, Wb, p.m_c, Wb, DQ);   // NOTE: `part` aliases the weight stage, see below
+      // ---------------- B4: pointer logits forward + backward: dz, dq^ (-> DQ), dz kept in su for B7
+      for (int m = warp; m < TM; m += NT / 32) {
+        float4 dqh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < cnt && s_live[m]) {
+          const int64_t b = base + m;
+          const float4 qh = *reinterpret_cast<const float4*>(DQ + m * E + lane * 4);
+          const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
+          for (int n0 = 0; n0 < N; n0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int n = n0 + i;
+              const float4 hv = (n < N) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[i] = fmaf(qh.x, hv.x, fmaf(qh.y, hv.y, fmaf(qh.z, hv.z, qh.w * hv.w)));
+            }
+            float sc = reduce8(v, lane);
+            int n = n0 + ((lane >> 2) & 7);
+            if ((lane & 3) == 0 && n < N) su[n] = 10.0f * tanhf(sc);
+          }
+          __syncwarp();
+          uint32_t mw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mw[i] = p.mask_hist[((int64_t)t * B + b) * 4 + i];
+          float u[4];
+          bool ok[4];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int n = lane * 4 + i;
+            ok[i] = n < N && !((mw[n >> 5] >> (n & 31)) & 1u);
+            u[i] = (n < N) ? su[n] : 0.f;
+            if (ok[i]) mx = fmaxf(mx, u[i]);
+          }
+          mx = warp_max(mx);
+          float ex[4], loc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ex[i] = ok[i] ? expf(u[i] - mx) : 0.f;
+            loc += ex[i];
+          }
+          const float inv = 1.0f / warp_sum(loc);
+          const float w = s_w[m];
+          const int act = s_act[m];
+          __syncwarp();
+          float* sc_z = SC + (size_t)m * 3 * QW + 2 * QW;   // dz[0..127] | q^[128..255]
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int n = lane * 4 + i;
+            // du = w (1[n==a] - pi_n);  dz = du * 10 (1 - tanh^2 z) = du * (10 - u^2 / 10)
+            float du = ok[i] ? w * ((n == act ? 1.f : 0.f) - ex[i] * inv) : 0.f;
+            float dz = du * (10.0f - 0.1f * u[i] * u[i]);
+            if (n < N) { su[n] = dz; sc_z[n] = dz; }
+          }
+          __syncwarp();
+          for (int n = 0; n < N; ++n) {
+            const float dz = su[n];
+            const float4 hv = __ldg(hp + n * (E / 4));
+            dqh.x = fmaf(dz, hv.x, dqh.x); dqh.y = fmaf(dz, hv.y, dqh.y);
+            dqh.z = fmaf(dz, hv.z, dqh.z); dqh.w = fmaf(dz, hv.w, dqh.w);
+          }
+          // dh_n += dz_n q^ is applied in B7 together with the glimpse terms (one RMW of dH per node and step)
+          *reinterpret_cast<float4*>(sc_z + 128 + lane * 4) = qh;
+        }
+        __syncwarp();
+        // every row of DQ must hold dq^ (zeros for idle instances) for the GEMMs below
+        *reinterpret_cast<float4*>(DQ + m * E + lane * 4) = dqh;
+      }
+      __syncthreads();
+      if (tid < E) {
+        float s = 0.f;
+        for (int m = 0; m < cnt; ++m) s += DQ[m * E + tid];
+        mc_acc += s;
+      }
+
+      // ---------------- B5: d m_t[k][e] += sum_m c[m][k] dq^[m][e]     (1024 x 128 outputs, K = 32)
+      {
+        const int tx = tid & 31, ty = tid >> 5;  // 16 k-groups of 64 rows, 4 columns per thread
+        for (int pass = 0; pass < 8; ++pass) {
+          const int k0 = ty * 64 + pass * 8;
+          float acc[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+          for (int m = 0; m < cnt; ++m) {
+            const float4 c0 = *reinterpret_cast<const float4*>(QC + m * QW + k0);
+            const float4 c1 = *reinterpret_cast<const float4*>(QC + m * QW + k0 + 4);
+            const float4 d = *reinterpret_cast<const float4*>(DQ + m * E + tx * 4);
+            const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              acc[i][0] = fmaf(cv[i], d.x, acc[i][0]); acc[i][1] = fmaf(cv[i], d.y, acc[i][1]);
+              acc[i][2] = fmaf(cv[i], d.z, acc[i][2]); acc[i][3] = fmaf(cv[i], d.w, acc[i][3]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            red_add4(p.d_m_t + (size_t)(k0 + i) * E + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        }
+      }
+      __syncthreads();
+
+      // ---------------- B6: dc = dq^ · M  -> QC (c is dead now)
+      tile_gemm_wide(DQ, p.m_n, Wb, [&](int m, int c, float4 v) { *reinterpret_cast<float4*>(QC + m * QW + c) = v; });
+      __syncthreads();
+
+      // ---------------- B7: glimpse backward per instance: dp, ds, dq~ (-> QC slot), dH += ...
+      for (int m = warp; m < TM; m += NT / 32) {
+        float* slot = QC + m * QW;
+        float4 dq[NH];
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) dq[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < cnt && s_live[m]) {
+          const int64_t b = base + m;
+          const float* sc_q = SC + (size_t)m * 3 * QW;
+          const float* sc_p = sc_q + QW;
+          const float* sc_z = sc_q + 2 * QW;
+          const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
+          float4 dc[NH];
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) dc[hh] = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
+          __syncwarp();
+          const int myh = (lane >> 2) & 7;
+          // dp_hn = dc_h · h_n  -> slot[h][n]
+          for (int n0 = 0; n0 < N; n0 += 4) {
+            float4 hv4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hv4[i] = (n0 + i < N) ? __ldg(hp + (n0 + i) * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = n0 + i;
+              if (n < N) {
+                const float4 hv = hv4[i];
+                float v[NH];
+#pragma unroll
+                for (int hh = 0; hh < NH; ++hh)
+                  v[hh] = fmaf(dc[hh].x, hv.x, fmaf(dc[hh].y, hv.y, fmaf(dc[hh].z, hv.z, dc[hh].w * hv.w)));
+                float sc = reduce8(v, lane);
+                if ((lane & 3) == 0) slot[myh * E + n] = sc;
+              }
+            }
+          }
+          __syncwarp();
+          // ds_hn = p_hn (dp_hn - sum_m p_hm dp_hm), lane = node
+          float ds[NH][4];
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) {
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              int n = lane + 32 * i;
+              float pv = (n < N) ? sc_p[n * 8 + hh] : 0.f;
+              float dp = (n < N) ? slot[hh * E + n] : 0.f;
+              ds[hh][i] = pv;       // p for now
+              dot = fmaf(pv, dp, dot);
+              // stash dp in place of ds after the dot product is known
+              if (n < N) slot[hh * E + n] = dp;
+            }
+            dot = warp_sum(dot);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              int n = lane + 32 * i;
+              float dp = (n < N) ? slot[hh * E + n] : 0.f;
+              ds[hh][i] = ds[hh][i] * (dp - dot);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int n = lane + 32 * i;
+            if (n < N) {
+              *reinterpret_cast<float4*>(slot + n * 8) = make_float4(ds[0][i], ds[1][i], ds[2][i], ds[3][i]);
+              *reinterpret_cast<float4*>(slot + n * 8 + 4) = make_float4(ds[4][i], ds[5][i], ds[6][i], ds[7][i]);
+            }
+          }
+          __syncwarp();
+          // pass Y: dH[b,n] += sum_h (p_hn dc_h + ds_hn q~_h) + dz_n q^     (one RMW of dH per node and step)
+          {
+            float4 qt[NH];
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) qt[hh] = *reinterpret_cast<const float4*>(sc_q + hh * E + lane * 4);
+            const float4 qh = *reinterpret_cast<const float4*>(sc_z + 128 + lane * 4);
+            float4* dhp = reinterpret_cast<float4*>(p.dH + b * N * E) + lane;
+            for (int n = 0; n < N; ++n) {
+              const float4 s0 = *reinterpret_cast<const float4*>(slot + n * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
+              const float4 p0 = *reinterpret_cast<const float4*>(sc_p + n * 8);
+              const float4 p1 = *reinterpret_cast<const float4*>(sc_p + n * 8 + 4);
+              const float dsv[NH] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float pv[NH] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+              const float dz = sc_z[n];
+              float4 g = make_float4(dz * qh.x, dz * qh.y, dz * qh.z, dz * qh.w);
+#pragma unroll
+              for (int hh = 0; hh < NH; ++hh) {
+                g.x = fmaf(pv[hh], dc[hh].x, fmaf(dsv[hh], qt[hh].x, g.x));
+                g.y = fmaf(pv[hh], dc[hh].y, fmaf(dsv[hh], qt[hh].y, g.y));
+                g.z = fmaf(pv[hh], dc[hh].z, fmaf(dsv[hh], qt[hh].z, g.z));
+                g.w = fmaf(pv[hh], dc[hh].w, fmaf(dsv[hh], qt[hh].w, g.w));
+              }
+              float4 o = dhp[n * (E / 4)];
+              dhp[n * (E / 4)] = make_float4(o.x + g.x, o.y + g.y, o.z + g.z, o.w + g.w);
+            }
+          }
+          // pass X: dq~_h = sum_n ds_hn h_n
+          for (int n = 0; n < N; ++n) {
+            const float4 hv = __ldg(hp + n * (E / 4));
+            const float4 s0 = *reinterpret_cast<const float4*>(slot + n * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
+            const float dsv[NH] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) {
+              dq[hh].x = fmaf(dsv[hh], hv.x, dq[hh].x); dq[hh].y = fmaf(dsv[hh], hv.y, dq[hh].y);
+              dq[hh].z = fmaf(dsv[hh], hv.z, dq[hh].z); dq[hh].w = fmaf(dsv[hh], hv.w, dq[hh].w);
+            }
+          }
+          // per-episode accumulators: D0 (t = 0) / D1 (t >= 1) / Dl (IRP)
+          float* Dacc = (t == 0 ? p.D0 : p.D1) + b * QW;
+          const float lf = s_loadf[m];
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) {
+            float4* dp4 = reinterpret_cast<float4*>(Dacc + hh * E + lane * 4);
+            float4 o = *dp4;
+            *dp4 = make_float4(o.x + dq[hh].x, o.y + dq[hh].y, o.z + dq[hh].z, o.w + dq[hh].w);
+            if (kind == VRPX_IRP) {
+              float4* dl4 = reinterpret_cast<float4*>(p.Dl + b * QW + hh * E + lane * 4);
+              float4 ol = *dl4;
+              *dl4 = make_float4(fmaf(lf, dq[hh].x, ol.x), fmaf(lf, dq[hh].y, ol.y), fmaf(lf, dq[hh].z, ol.z),
+                                 fmaf(lf, dq[hh].w, ol.w));
+            }
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) *reinterpret_cast<float4*>(slot + hh * E + lane * 4) = dq[hh];
+      }
+      __syncthreads();
+
+      if (t > 0) {
+        // ---------------- B8: d al_t[j][c] += sum_m x_l[m][j] dq~[m][c]     (128 x 1024 outputs, K = 32)
+        {
+          const int tx = tid & 127, ty = tid >> 7;  // 4 j-groups of 32 rows, 4 columns per thread per half
+          for (int pass = 0; pass < 8; ++pass) {
+            const int j0 = ty * 32 + (pass >> 1) * 8, c0 = (pass & 1) * 512 + tx * 4;
+            float acc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int m = 0; m < cnt; ++m) {
+              const float4 x0 = *reinterpret_cast<const float4*>(Xs + m * E + j0);
+              const float4 x1 = *reinterpret_cast<const float4*>(Xs + m * E + j0 + 4);
+              const float4 d = *reinterpret_cast<const float4*>(QC + m * QW + c0);
+              const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                acc[i][0] = fmaf(xv[i], d.x, acc[i][0]); acc[i][1] = fmaf(xv[i], d.y, acc[i][1]);
+                acc[i][2] = fmaf(xv[i], d.z, acc[i][2]); acc[i][3] = fmaf(xv[i], d.w, acc[i][3]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              red_add4(p.d_al_t + (size_t)(j0 + i) * QW + c0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+          }
+        }
+        __syncthreads();
+        // ---------------- B9: dx_l = dq~ · A_l -> DQ, then dH[b, last] += dx_l
+        tile_gemm_tall(QC, p.al_n, Wb, nullptr, Wb, DQ);
+        for (int m = warp; m < cnt; m += NT / 32) {
+          if (!s_live[m]) continue;
+          const int64_t b = base + m;
+          float4* dhp = reinterpret_cast<float4*>(p.dH + (b * N + s_prev[m]) * E) + lane;
+          const float4 g = *reinterpret_cast<const float4*>(DQ + m * E + lane * 4);
+          float4 o = *dhp;
+          *dhp = make_float4(o.x + g.x, o.y + g.y, o.z + g.z, o.w + g.w);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < E) atomicAdd(p.d_m_c + tid, mc_acc);
+}
+
+// ---------------------------------------------------------------- small epilogue helpers (per episode, not per step)
+// C[M][N] += A^T · Bm with A [R][M], Bm [R][N] row-major: reduction over rows, split across CTAs, red.add epilogue.
+// Used for weight gradients (dW = dY^T X) in the decoder epilogue and the encoder backward.  64x64 output tile.
+__global__ void __launch_bounds__(256) k_gemm_tn_atomic(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                         float* __restrict__ C, int64_t R, int M, int N,
+                                                         int64_t rows_per_cta) {
+  __shared__ __align__(16) float As[16][64 + 4], Bs[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.z * 64;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = (r_begin + rows_per_cta < R) ? r_begin + rows_per_cta : R;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;  // loader: row lr (0..15), 4 columns at lc
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += 16) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    if (r0 + lr < r_end) {
+      if (m0 + lc < M) av = *reinterpret_cast<const float4*>(A + (r0 + lr) * M + m0 + lc);
+      if (n0 + lc < N) bv = *reinterpret_cast<const float4*>(Bm + (r0 + lr) * N + n0 + lc);
+    }
+    *reinterpret_cast<float4*>(&As[lr][lc]) = av;
+    *reinterpret_cast<float4*>(&Bs[lr][lc]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) atomicAdd(C + (size_t)m * N + n, acc[i][j]);
+    }
+  }
+}
+
+// out[c] += sum_r X[r][c]   (C <= 1024 columns, any R)
+__global__ void __launch_bounds__(256) k_colsum_atomic(const float* __restrict__ X, int64_t R, int Ccols,
+                                                        float* __restrict__ out, int64_t rows_per_cta) {
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = (r_begin + rows_per_cta < R) ? r_begin + rows_per_cta : R;
+  for (int c = threadIdx.x; c < Ccols; c += 256) {
+    float s = 0.f;
+    for (int64_t r = r_begin; r < r_end; ++r) s += X[r * Ccols + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+// Per-episode decoder terms: G[b] = mean_n h[b,n]; Xf[b] = h[b, tape[0][b]]   (one warp per instance)
+__global__ void __launch_bounds__(256) k_episode_gather(const float* __restrict__ h, const uint8_t* __restrict__ tape,
+                                                         int64_t B, int N, float* __restrict__ G, float* __restrict__ Xf) {
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n = 0; n < N; ++n) {
+    float4 v = __ldg(hp + n * (E / 4));
+    g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+  }
+  const float inv = 1.0f / (float)N;
+  reinterpret_cast<float4*>(G + b * E)[lane] = make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv);
+  if (Xf) reinterpret_cast<float4*>(Xf + b * E)[lane] = __ldg(hp + (int)tape[b] * (E / 4));
+}
+
+// dH[b,n] += dG[b] / N for every n;  dH[b, tape[0][b]] += dXf[b]
+__global__ void __launch_bounds__(256) k_episode_scatter(float* __restrict__ dH, const uint8_t* __restrict__ tape,
+                                                          int64_t B, int N, const float* __restrict__ dG,
+                                                          const float* __restrict__ dXf) {
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float4* dp = reinterpret_cast<float4*>(dH + b * N * E) + lane;
+  const float4 g = reinterpret_cast<const float4*>(dG + b * E)[lane];
+  const float inv = 1.0f / (float)N;
+  const int first = dXf ? (int)tape[b] : -1;
+  float4 xf = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dXf) xf = reinterpret_cast<const float4*>(dXf + b * E)[lane];
+  for (int n = 0; n < N; ++n) {
+    float4 o = dp[n * (E / 4)];
+    o.x += g.x * inv; o.y += g.y * inv; o.z += g.z * inv; o.w += g.w * inv;
+    if (n == first) { o.x += xf.x; o.y += xf.y; o.z += xf.z; o.w += xf.w; }
+    dp[n * (E / 4)] = o;
+  }
+}
+
+}  // namespace vrpx
+
+using namespace vrpx;
+
+extern "C" {
+
+int64_t vrpx_decoder_backward_workspace_bytes(int64_t B, int32_t N) {
+  (void)N;
+  int64_t grid = (B + TM - 1) / TM;
+  if (grid > num_sms()) grid = num_sms();
+  return grid * (int64_t)TM * 3 * QW * (int64_t)sizeof(float);
+}
+
+int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, const vrpx_decoder_bwd_weights* wb,
+                          const float* h, const uint8_t* tape, int32_t T, int64_t coupling,
+                          const vrpx_rollout_trace* trace, const float* qg, const float* wts,
+                          const vrpx_decoder_grads* g, void* ws, int64_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VRPX_CHECK_ARG(env && w && wb && h && tape && trace && qg && wts && g && ws, "NULL argument");
+  VRPX_CHECK_ARG(env->N >= 2 && env->N <= VRPX_MAX_NODES && env->B >= 1 && T >= 1, "bad shape");
+  VRPX_CHECK_ARG(trace->mask_hist && trace->qg0 && (env->kind != VRPX_IRP || trace->load_hist), "trace incomplete");
+  VRPX_CHECK_ARG(g->dH && g->D0 && g->D1 && g->d_al_t && g->d_m_t && g->d_m_c && (env->kind != VRPX_IRP || g->Dl),
+                 "gradient buffers");
+  VRPX_CHECK_ARG(ws_bytes >= vrpx_decoder_backward_workspace_bytes(env->B, env->N), "workspace too small");
+  DecBwdParams p;
+  p.kind = env->kind; p.N = env->N; p.T = T; p.B = env->B; p.G = coupling;
+  p.h = h; p.tape = tape; p.mask_hist = trace->mask_hist; p.load_hist = trace->load_hist;
+  p.qg0 = trace->qg0; p.qg = qg; p.wts = wts;
+  p.al_t = w->al_t; p.a_q0 = w->a_q0; p.a_load = w->a_load; p.m_t = w->m_t; p.m_c = w->m_c;
+  p.m_n = wb->m_n; p.al_n = wb->al_n;
+  p.dH = g->dH; p.D0 = g->D0; p.D1 = g->D1; p.Dl = g->Dl; p.d_al_t = g->d_al_t; p.d_m_t = g->d_m_t; p.d_m_c = g->d_m_c;
+  p.scratch = reinterpret_cast<float*>(ws);
+  int64_t ntiles = (env->B + TM - 1) / TM;
+  int grid = (int)((ntiles < (int64_t)num_sms()) ? ntiles : (int64_t)num_sms());
+  VRPX_CUDA(cudaFuncSetAttribute(k_decoder_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  k_decoder_bwd<<<grid, NT, BWD_SMEM, stream>>>(p);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R, int32_t M, int32_t N, void* stream) {
+  VRPX_CHECK_ARG(A && Bm && C && R >= 1 && M >= 1 && N >= 1 && M % 4 == 0 && N % 4 == 0, "bad argument");
+  int64_t ctas = (R + 2047) / 2048;
+  int64_t maxc = (int64_t)num_sms() * 8;
+  if (ctas > maxc) ctas = maxc;
+  int64_t rows = ((R + ctas - 1) / ctas + 15) / 16 * 16;
+  ctas = (R + rows - 1) / rows;
+  dim3 grid((unsigned)ctas, (unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+  k_gemm_tn_atomic<<<grid, 256, 0, (cudaStream_t)stream>>>(A, Bm, C, R, M, N, rows);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out, void* stream) {
+  VRPX_CHECK_ARG(X && out && R >= 1 && Ccols >= 1, "bad argument");
+  int64_t ctas = (R + 511) / 512;
+  int64_t maxc = (int64_t)num_sms() * 8;
+  if (ctas > maxc) ctas = maxc;
+  int64_t rows = (R + ctas - 1) / ctas;
+  ctas = (R + rows - 1) / rows;
+  k_colsum_atomic<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(X, R, Ccols, out, rows);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B, int32_t N, float* G, float* Xf, void* stream) {
+  VRPX_CHECK_ARG(h && G && B >= 1 && (Xf == nullptr || tape0 != nullptr), "bad argument");
+  k_episode_gather<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(h, tape0, B, N, G, Xf);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+int vrpx_episode_scatter(float* dH, const uint8_t* tape0, int64_t B, int32_t N, const float* dG, const float* dXf,
+                         void* stream) {
+  VRPX_CHECK_ARG(dH && dG && B >= 1 && (dXf == nullptr || tape0 != nullptr), "bad argument");
+  k_episode_scatter<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dH, tape0, B, N, dG, dXf);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+}  // extern "C"

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float y = acc[i][j];
+      if (a.gate && !(a.gate[r * a.NOUT + c + j] > 0.f)) y = 0.f;
       if (a.bias) y += a.bias[c + j];
       if (a.relu) y = fmaxf(y, 0.f);
       if (a.residual) y += a.residual[r * a.NOUT + c + j];
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float* __restrict__ y, i
 // Fold statistics + affine into y*scale + shift.  train: batch stats (biased var for normalisation,
 // unbiased for the running update, momentum 0.1); eval: running stats.  128 threads.
 __global__ void k_bn_fold(BnSlots* slot, const float* __restrict__ w, const float* __restrict__ b,
-                          float* run_mean, float* run_var, int train, int64_t R) {
+                          float* run_mean, float* run_var, int train, int64_t R, float* stat_out) {
   int c = threadIdx.x;
   float mean, var;
   if (train) {
@@ -235,6 +236,10 @@ __global__ void k_bn_fold(BnSlots* slot, const float* __restrict__ w, const floa
     var = run_var[c];
   }
   float invstd = 1.0f / sqrtf(var + 1e-5f);
+  if (stat_out) {  // saved for the backward pass: batch mean and 1/sqrt(var + eps)
+    stat_out[c] = mean;
+    stat_out[E + c] = invstd;
+  }
   float alpha = invstd * w[c];
   slot->scale[c] = alpha;
   slot->shift[c] = b[c] - mean * alpha;
@@ -255,6 +260,11 @@ __global__ void k_affine(const float* __restrict__ y, const BnSlots* __restrict_
 
 constexpr int64_t kSmallWs = 32768;          // 6 BnSlots (3 KiB each) rounded up
 constexpr int64_t kRowBytes = (512 + 128) * 4;  // qkv|att (or ff hidden) + pre-BN y, per row
+// Activations saved for the backward pass (train mode), per row of R = B*N:
+//   H[0..2] (inputs of the three layers) | per layer: QKV 384, ATT 128, Y1 128, H1 128, F 512, Y2 128
+constexpr int64_t kSavedLayerFloats = 384 + 128 + 128 + 128 + 512 + 128;           // 1408
+constexpr int64_t kSavedRowFloats = 3 * 128 + VRPX_LAYERS * kSavedLayerFloats;     // 4608
+constexpr int64_t kSavedStatFloats = 2 * VRPX_LAYERS * 2 * 128;                    // 6 x (mean, invstd)
 
 }  // namespace vrpx
 
@@ -264,11 +274,16 @@ extern "C" {
 
 int64_t vrpx_encoder_workspace_bytes(int64_t B, int32_t N) { return kSmallWs + B * (int64_t)N * kRowBytes; }
 
+int64_t vrpx_encoder_saved_bytes(int64_t B, int32_t N) {
+  return (B * (int64_t)N * kSavedRowFloats + kSavedStatFloats) * (int64_t)sizeof(float);
+}
+
 int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, const float* x,
                          const int32_t* depot, int64_t B, int32_t N, int32_t train, float* h, void* ws,
-                         int64_t ws_bytes, int32_t gemm_path, void* stream_) {
+                         int64_t ws_bytes, int32_t gemm_path, float* saved, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(w && h && ws, "weights / h / ws must be non-NULL");
+  VRPX_CHECK_ARG(!saved || train, "activations are only saved in train mode");
   VRPX_CHECK_ARG(B >= 1 && N >= 1 && N <= VRPX_MAX_NODES, "bad B or N");
   VRPX_CHECK_ARG(w->f == 2 || w->f == 3, "node feature count must be 2 or 3");
   VRPX_CHECK_ARG(x || (env && env->xy && (w->f == 2 || env->demand)), "need x or an env with features");
@@ -290,9 +305,9 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
   if (!train) {
     for (int l = 0; l < VRPX_LAYERS; ++l) {
       const vrpx_encoder_layer& L = w->layer[l];
-      k_bn_fold<<<1, E, 0, stream>>>(slots + 2 * l, L.bn1_w, L.bn1_b, L.bn1_mean, L.bn1_var, 0, 0);
+      k_bn_fold<<<1, E, 0, stream>>>(slots + 2 * l, L.bn1_w, L.bn1_b, L.bn1_mean, L.bn1_var, 0, 0, nullptr);
       VRPX_LAUNCH_CHECK();
-      k_bn_fold<<<1, E, 0, stream>>>(slots + 2 * l + 1, L.bn2_w, L.bn2_b, L.bn2_mean, L.bn2_var, 0, 0);
+      k_bn_fold<<<1, E, 0, stream>>>(slots + 2 * l + 1, L.bn2_w, L.bn2_b, L.bn2_mean, L.bn2_var, 0, 0, nullptr);
       VRPX_LAUNCH_CHECK();
     }
   }
@@ -304,6 +319,8 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
     float* att = big + R * 384;       // [R][128]
     float* hid = big;                 // [R][512]  (aliases qkv|att, which are dead by then)
     float* ybuf = big + R * 512;      // [R][128]  pre-BN activations (train)
+    float* sv_stats = saved ? saved + R * kSavedRowFloats : nullptr;
+    if (saved) hc = saved;            // H[0]: the embedding is the input of layer 0
     {
       int64_t n = R * (E / 4);
       k_embed<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
@@ -316,6 +333,14 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
       const vrpx_encoder_layer& L = w->layer[l];
       BnSlots* s1 = slots + 2 * l;
       BnSlots* s2 = slots + 2 * l + 1;
+      float* h1 = hc;   // output of BN1 (in place unless activations are saved)
+      float* hout = hc; // output of BN2 = input of the next layer
+      float *y1 = ybuf, *y2 = ybuf;
+      if (saved) {
+        float* Lb = saved + R * 384 + (int64_t)l * R * kSavedLayerFloats;
+        qkv = Lb; att = Lb + R * 384; y1 = Lb + R * 512; h1 = Lb + R * 640; hid = Lb + R * 768; y2 = Lb + R * 1280;
+        hout = (l + 1 < VRPX_LAYERS) ? saved + (int64_t)(l + 1) * R * 128 : h + b0 * N * E;
+      }
       int rc;
       GemmArgs g1{hc, R, E, L.in_proj_w, 3 * E, L.in_proj_b, 0, nullptr, nullptr, nullptr, qkv};
       if ((rc = gemm(g1, stream))) return rc;
@@ -325,30 +350,33 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
         GemmArgs g2{att, R, E, L.out_proj_w, E, L.out_proj_b, 0, hc, s1->scale, s1->shift, hc};
         if ((rc = gemm(g2, stream))) return rc;
       } else {
-        GemmArgs g2{att, R, E, L.out_proj_w, E, L.out_proj_b, 0, hc, nullptr, nullptr, ybuf};
+        GemmArgs g2{att, R, E, L.out_proj_w, E, L.out_proj_b, 0, hc, nullptr, nullptr, y1};
         if ((rc = gemm(g2, stream))) return rc;
-        k_bn_stats<<<num_sms() * 4, 256, 0, stream>>>(ybuf, R, s1);
+        k_bn_stats<<<num_sms() * 4, 256, 0, stream>>>(y1, R, s1);
         VRPX_LAUNCH_CHECK();
-        k_bn_fold<<<1, E, 0, stream>>>(s1, L.bn1_w, L.bn1_b, L.bn1_mean, L.bn1_var, 1, R);
+        k_bn_fold<<<1, E, 0, stream>>>(s1, L.bn1_w, L.bn1_b, L.bn1_mean, L.bn1_var, 1, R,
+                                       sv_stats ? sv_stats + (2 * l) * 256 : nullptr);
         VRPX_LAUNCH_CHECK();
-        k_affine<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(ybuf, s1, R * 32, hc);
+        k_affine<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(y1, s1, R * 32, h1);
         VRPX_LAUNCH_CHECK();
       }
-      GemmArgs g3{hc, R, E, L.ff0_w, FF, L.ff0_b, 1, nullptr, nullptr, nullptr, hid};
+      GemmArgs g3{h1, R, E, L.ff0_w, FF, L.ff0_b, 1, nullptr, nullptr, nullptr, hid};
       if ((rc = gemm(g3, stream))) return rc;
       if (!train) {
         GemmArgs g4{hid, R, FF, L.ff2_w, E, L.ff2_b, 0, hc, s2->scale, s2->shift, hc};
         if ((rc = gemm(g4, stream))) return rc;
       } else {
-        GemmArgs g4{hid, R, FF, L.ff2_w, E, L.ff2_b, 0, hc, nullptr, nullptr, ybuf};
+        GemmArgs g4{hid, R, FF, L.ff2_w, E, L.ff2_b, 0, h1, nullptr, nullptr, y2};
         if ((rc = gemm(g4, stream))) return rc;
-        k_bn_stats<<<num_sms() * 4, 256, 0, stream>>>(ybuf, R, s2);
+        k_bn_stats<<<num_sms() * 4, 256, 0, stream>>>(y2, R, s2);
         VRPX_LAUNCH_CHECK();
-        k_bn_fold<<<1, E, 0, stream>>>(s2, L.bn2_w, L.bn2_b, L.bn2_mean, L.bn2_var, 1, R);
+        k_bn_fold<<<1, E, 0, stream>>>(s2, L.bn2_w, L.bn2_b, L.bn2_mean, L.bn2_var, 1, R,
+                                       sv_stats ? sv_stats + (2 * l + 1) * 256 : nullptr);
         VRPX_LAUNCH_CHECK();
-        k_affine<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(ybuf, s2, R * 32, hc);
+        k_affine<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(y2, s2, R * 32, hout);
         VRPX_LAUNCH_CHECK();
       }
+      hc = hout;
     }
   }
   return VRPX_OK;

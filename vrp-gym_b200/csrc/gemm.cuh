@@ -6,7 +6,7 @@
 namespace vrpx {
 
 // Y[R][NOUT] = epilogue( X[R][K] · W[NOUT][K]^T )      (W in torch nn.Linear layout)
-// epilogue order: acc + bias -> relu -> + residual -> * scale + shift
+// epilogue order: acc * (gate > 0) -> + bias -> relu -> + residual -> * scale + shift
 struct GemmArgs {
   const float* X;
   int64_t R;
@@ -19,6 +19,7 @@ struct GemmArgs {
   const float* scale;     // [NOUT] or nullptr  (eval-mode BatchNorm folded affine)
   const float* shift;     // [NOUT] or nullptr
   float* Y;
+  const float* gate = nullptr;  // [R][NOUT] or nullptr: ReLU-backward gate (acc is zeroed where gate <= 0)
 };
 
 int gemm_simt(const GemmArgs& a, cudaStream_t stream);  // fp32 FFMA, smem tiled

@@ -167,15 +167,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc(GemmArgs a) {
       const int c0 = col0 + cbase;
       float* yrow = a.Y + r * a.NOUT + c0;
       const float* rrow = a.residual ? a.residual + r * a.NOUT + c0 : nullptr;
+      const float* grow = a.gate ? a.gate + r * a.NOUT + c0 : nullptr;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float o[4];
         float4 res = rrow ? *reinterpret_cast<const float4*>(rrow + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float rr[4] = {res.x, res.y, res.z, res.w};
+        float4 gt = grow ? *reinterpret_cast<const float4*>(grow + 4 * q) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float gg[4] = {gt.x, gt.y, gt.z, gt.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = c0 + 4 * q + e;
           float y = __uint_as_float(v[4 * q + e]);
+          if (!(gg[e] > 0.f)) y = 0.f;
           if (a.bias) y += __ldg(a.bias + c);
           if (a.relu) y = fmaxf(y, 0.f);
           y += rr[e];

@@ -15,18 +15,9 @@
 //
 // Step-invariant work the reference repeats every step (K/V/kp projections, graph mean) is folded into
 // host-packed weights (vrpx/packing.py) and the per-episode Q~g table built in the prologue.
-#include "env_rules.cuh"
+#include "tile_gemm.cuh"
 
 namespace vrpx {
-
-constexpr int TM = 32;        // instances per tile
-constexpr int NT = 512;       // threads per CTA (16 warps; <= 128 registers per thread)
-constexpr int QW = NH * E;    // 1024: per-instance width of q~ / c
-constexpr size_t SMEM_X = (size_t)TM * E * sizeof(float);    // 16 KiB
-constexpr size_t SMEM_QC = (size_t)TM * QW * sizeof(float);  // 128 KiB
-constexpr int WCHUNK_FLOATS = 16 * 512;                      // one staged weight chunk: 32 KiB
-constexpr size_t SMEM_W = 2 * (size_t)WCHUNK_FLOATS * sizeof(float);  // double buffer, 64 KiB
-constexpr size_t SMEM_TOTAL = SMEM_X + SMEM_QC + SMEM_W;
 
 struct RolloutParams {
   vrpx_env env;
@@ -43,229 +34,14 @@ struct RolloutParams {
   int* steps;
   float* logits;
   float* qg;          // [B][1024]
+  float* qg0;         // optional copy of Q~g before the `first` fold (backward)
+  uint32_t* mask_hist;  // optional [Tmax][B][4] decoder-visible mask before each step (backward)
+  float* load_hist;   // optional [Tmax][B] f32 vehicle load before each step (backward)
   unsigned* bar;      // grid barrier counter
   int* notdone;       // [Tmax + 1]
 };
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ int ld_acquire_i(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (ld_acquire(bar) < target) __nanosleep(32);
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// Sum 8 per-lane values across the warp; lane l returns the total of v[(l >> 2) & 7].
-__device__ __forceinline__ float reduce8(const float v[8], int lane) {
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-  float w4[4], w2[2], x;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
-    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float keep = b3 ? w4[i + 2] : w4[i], send = b3 ? w4[i] : w4[i + 2];
-    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  {
-    float keep = b2 ? w2[1] : w2[0], send = b2 ? w2[0] : w2[1];
-    x = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  x += __shfl_xor_sync(0xffffffffu, x, 2);
-  x += __shfl_xor_sync(0xffffffffu, x, 1);
-  return x;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// ---------------------------------------------------------------- GEMM-A: [TM x 128] · [128 x 1024]
-// Xs smem [TM][128]; Wt global [128][1024], streamed through a double-buffered smem stage with cp.async in
-// chunks of 16 k-rows x 512 columns (32 KiB).  512 threads = 4 row groups x 128 column threads; each thread owns
-// 8 rows x 4 columns {4tx..4tx+3} of the current 512-column half (conflict-free LDS.128).
-// EPI 0: qg[b][c] = acc + a_c[c]               (prologue: graph-embedding term + bias)
-// EPI 1: qg[b][c] += acc                       (step 1: `first` term, graph_decoder.py:111-113)
-// EPI 2: QC[m][c] = acc + qg[b][c] + loadf[m] * a_load[c]
-__device__ __forceinline__ void stage_a_chunk(const float* __restrict__ Wt, int chunk, float* __restrict__ dst) {
-  const int half = chunk >> 3, k0 = (chunk & 7) * 16;
-  const float* src = Wt + (size_t)k0 * QW + half * 512;
-#pragma unroll
-  for (int i = 0; i < 2048 / NT; ++i) {
-    int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
-    int r = idx >> 7, c4 = idx & 127;
-    cp_async16(dst + r * 512 + c4 * 4, src + (size_t)r * QW + c4 * 4);
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void gemm_a(const float* __restrict__ Xs, const float* __restrict__ Wt,
-                                       float* __restrict__ QC, float* __restrict__ Wb, const RolloutParams& p,
-                                       int64_t base, int cnt, const float* __restrict__ loadf) {
-  const int tid = threadIdx.x, ty = tid >> 7, tx = tid & 127;
-  stage_a_chunk(Wt, 0, Wb);
-  cp_async_commit();
-  float acc[8][4];
-  for (int chunk = 0; chunk < 16; ++chunk) {
-    const int half = chunk >> 3, k0 = (chunk & 7) * 16;
-    if ((chunk & 7) == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    }
-    if (chunk + 1 < 16) {
-      stage_a_chunk(Wt, chunk + 1, Wb + ((chunk + 1) & 1) * WCHUNK_FLOATS);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const float* wb = Wb + (chunk & 1) * WCHUNK_FLOATS + tx * 4;
-#pragma unroll
-    for (int kq = 0; kq < 16; kq += 4) {
-      float4 xv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty * 8 + i) * E + k0 + kq);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * 512);
-        const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
-        }
-      }
-    }
-    __syncthreads();  // the stage may be refilled by the next iteration's cp.async
-    if ((chunk & 7) == 7) {
-      const int c = half * 512 + tx * 4;
-      float4 ac = make_float4(0.f, 0.f, 0.f, 0.f), al = ac;
-      if (EPI == 0) ac = *reinterpret_cast<const float4*>(p.w.a_c + c);
-      if (EPI == 2 && p.env.kind == VRPX_IRP) al = *reinterpret_cast<const float4*>(p.w.a_load + c);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = ty * 8 + i;
-        if (m >= cnt) continue;
-        const int64_t b = base + m;
-        float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        float4* qgp = reinterpret_cast<float4*>(p.qg + b * QW + c);
-        if (EPI == 0) {
-          *qgp = make_float4(v.x + ac.x, v.y + ac.y, v.z + ac.z, v.w + ac.w);
-        } else if (EPI == 1) {
-          float4 q = *qgp;
-          *qgp = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
-        } else {
-          const float4 q = *qgp;
-          v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
-          if (p.env.kind == VRPX_IRP) {
-            const float lf = loadf[m];
-            v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
-          }
-          *reinterpret_cast<float4*>(QC + m * QW + c) = v;
-        }
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------- GEMM-B: [TM x 1024] · [1024 x 128]
-// C smem [TM][1024]; Mt global [1024][128] staged with cp.async: chunk kc = rows {kg*256 + kc*16 + r} of the four
-// k-groups (4 x 16 rows x 128 columns = 32 KiB).  512 threads = 4 k-groups x 4 row groups x 32 column threads,
-// 8 rows x 4 columns {4tx..+3} each over a quarter of K; partial sums reduced through smem.
-// Result q^[m][e] (+ m_c) is written to Xs[TM][128].
-__device__ __forceinline__ void stage_b_chunk(const float* __restrict__ Mt, int kc, float* __restrict__ dst) {
-#pragma unroll
-  for (int i = 0; i < 2048 / NT; ++i) {
-    int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
-    int row = idx >> 5, c4 = idx & 31;    // row in [0,64): kg = row >> 4, r = row & 15
-    int k = (row >> 4) * 256 + kc * 16 + (row & 15);
-    cp_async16(dst + row * E + c4 * 4, Mt + (size_t)k * E + c4 * 4);
-  }
-}
-
-__device__ __forceinline__ void gemm_b(float* __restrict__ QC, float* __restrict__ Xs, float* __restrict__ Wb,
-                                       const RolloutParams& p) {
-  const int tid = threadIdx.x, kg = tid >> 7, ty = (tid >> 5) & 3, tx = tid & 31;
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  stage_b_chunk(p.w.m_t, 0, Wb);
-  cp_async_commit();
-  for (int kc = 0; kc < 16; ++kc) {
-    if (kc + 1 < 16) {
-      stage_b_chunk(p.w.m_t, kc + 1, Wb + ((kc + 1) & 1) * WCHUNK_FLOATS);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const float* wb = Wb + (kc & 1) * WCHUNK_FLOATS + kg * 16 * E + tx * 4;
-    const int k0 = kg * 256 + kc * 16;
-#pragma unroll
-    for (int kq = 0; kq < 16; kq += 4) {
-      float4 xv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(QC + (ty * 8 + i) * QW + k0 + kq);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * E);
-        const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
-        }
-      }
-    }
-    __syncthreads();  // also orders the last reads of C before the partials overwrite it
-  }
-  float* part = QC;  // [4][TM][128]
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(part + (kg * TM + ty * 8 + i) * E + tx * 4) =
-        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  __syncthreads();
-  for (int o = tid; o < TM * E; o += NT) {
-    float s = part[o] + part[TM * E + o] + part[2 * TM * E + o] + part[3 * TM * E + o];
-    Xs[o] = s + p.w.m_c[o & (E - 1)];
-  }
-  __syncthreads();
-}
-
-// glimpse-mask source row for attention row (b, hh): mask.repeat(H,1) indexing (graph_decoder.py:93)
-__device__ __forceinline__ int64_t quirk_row(int64_t b, int hh, long long G) {
-  if (G <= 0) return b;
-  int64_t g0 = (b / G) * G;
-  return g0 + (((b - g0) * NH + hh) % G);
-}
+constexpr size_t SMEM_TOTAL = SMEM_X + SMEM_QC + SMEM_W;
 
 // ---------------------------------------------------------------- the persistent kernel
 __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
@@ -301,7 +77,13 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       *reinterpret_cast<float4*>(Xs + m * E + lane * 4) = g;
     }
     __syncthreads();
-    gemm_a<0>(Xs, p.w.ag_t, QC, Wb, p, base, cnt, s_loadf);
+    tile_gemm_wide(Xs, p.w.ag_t, Wb, [&](int m, int c, float4 v) {   // Q~g = A_g · g + a_c
+      if (m >= cnt) return;
+      const float4 ac = *reinterpret_cast<const float4*>(p.w.a_c + c);
+      v = make_float4(v.x + ac.x, v.y + ac.y, v.z + ac.z, v.w + ac.w);
+      *reinterpret_cast<float4*>(p.qg + (base + m) * QW + c) = v;
+      if (p.qg0) *reinterpret_cast<float4*>(p.qg0 + (base + m) * QW + c) = v;
+    });
     __syncthreads();
   }
 
@@ -321,7 +103,11 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           xv = __ldg(reinterpret_cast<const float4*>(h + ((base + m) * N + last) * E) + lane);
         }
         *reinterpret_cast<float4*>(Xs + m * E + lane * 4) = xv;
-        if (lane == 0) s_loadf[m] = (m < cnt) ? (float)p.env.load[base + m] : 0.f;
+        const float lf = (m < cnt) ? (float)p.env.load[base + m] : 0.f;
+        if (lane == 0) s_loadf[m] = lf;
+        if (m < cnt && p.mask_hist && lane < 4)
+          p.mask_hist[((int64_t)trel * B + base + m) * 4 + lane] = __ldcg(p.env.mask + (base + m) * 4 + lane);
+        if (m < cnt && p.load_hist && lane == 0) p.load_hist[(int64_t)trel * B + base + m] = lf;
       }
       __syncthreads();
       // ---------------- P1: q~
@@ -334,10 +120,25 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         }
       } else {
         if (t == 1 && kind != VRPX_IRP) {
-          gemm_a<1>(Xs, p.w.af_t, QC, Wb, p, base, cnt, s_loadf);
+          tile_gemm_wide(Xs, p.w.af_t, Wb, [&](int m, int c, float4 v) {   // fold `first` (graph_decoder.py:111-113)
+            if (m >= cnt) return;
+            float4* qgp = reinterpret_cast<float4*>(p.qg + (base + m) * QW + c);
+            const float4 q = *qgp;
+            *qgp = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
+          });
           __syncthreads();  // qg updates are re-read by other threads' epilogue below? (same thread) — keep ordering explicit
         }
-        gemm_a<2>(Xs, p.w.al_t, QC, Wb, p, base, cnt, s_loadf);
+        tile_gemm_wide(Xs, p.w.al_t, Wb, [&](int m, int c, float4 v) {   // q~ = A_l · h[last] + Q~g (+ load · a_load)
+          if (m >= cnt) return;
+          const float4 q = *reinterpret_cast<const float4*>(p.qg + (base + m) * QW + c);
+          v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+          if (kind == VRPX_IRP) {
+            const float4 al = *reinterpret_cast<const float4*>(p.w.a_load + c);
+            const float lf = s_loadf[m];
+            v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
+          }
+          *reinterpret_cast<float4*>(QC + m * QW + c) = v;
+        });
       }
       __syncthreads();
 
@@ -466,7 +267,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       __syncthreads();
 
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
-      gemm_b(QC, Xs, Wb, p);
+      tile_gemm_tall(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs);
 
       // ---------------- P4: logits, action, environment transition
       bool unfinished = false;
@@ -620,8 +421,8 @@ int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N) {
 
 int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float* h, int32_t mode,
                  int64_t coupling, uint64_t seed, uint64_t offset, uint8_t* tape, int32_t t_begin, int32_t Tmax,
-                 float* logp, float* cost, int32_t* steps, float* logits, void* ws, int64_t ws_bytes,
-                 void* stream_) {
+                 float* logp, float* cost, int32_t* steps, float* logits, const vrpx_rollout_trace* trace,
+                 void* ws, int64_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(env && w && h && logp && cost && steps && ws, "NULL argument");
   VRPX_CHECK_ARG(env->kind >= 0 && env->kind <= 2 && env->N >= 2 && env->N <= VRPX_MAX_NODES && env->B >= 1,
@@ -651,6 +452,9 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   p.cost = cost;
   p.steps = steps;
   p.logits = logits;
+  p.qg0 = trace ? trace->qg0 : nullptr;
+  p.mask_hist = trace ? trace->mask_hist : nullptr;
+  p.load_hist = trace ? trace->load_hist : nullptr;
   p.bar = reinterpret_cast<unsigned*>(ws);
   p.notdone = reinterpret_cast<int*>(ws) + 8;
   p.qg = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kRolloutSmall);

@@ -1,0 +1,210 @@
+// tile_gemm.cuh — CTA-level building blocks shared by the persistent rollout kernel (rollout.cu) and the
+// recompute-based decoder backward (decoder_bwd.cu): a tile of TM = 32 instances, 512 threads, fp32 FFMA
+// register tiles, shared weights streamed from L2 through a cp.async double buffer.
+#pragma once
+#include "env_rules.cuh"
+
+namespace vrpx {
+
+constexpr int TM = 32;        // instances per tile
+constexpr int NT = 512;       // threads per CTA (16 warps; <= 128 registers per thread)
+constexpr int QW = NH * E;    // 1024: per-instance width of q~ / c
+constexpr size_t SMEM_X = (size_t)TM * E * sizeof(float);    // 16 KiB
+constexpr size_t SMEM_QC = (size_t)TM * QW * sizeof(float);  // 128 KiB
+constexpr int WCHUNK_FLOATS = 16 * 512;                      // one staged weight chunk: 32 KiB
+constexpr size_t SMEM_W = 2 * (size_t)WCHUNK_FLOATS * sizeof(float);  // double buffer, 64 KiB
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_acquire_i(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire(bar) < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Sum 8 per-lane values across the warp; lane l returns the total of v[(l >> 2) & 7].
+__device__ __forceinline__ float reduce8(const float v[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float w4[4], w2[2], x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float keep = b3 ? w4[i + 2] : w4[i], send = b3 ? w4[i] : w4[i + 2];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    float keep = b2 ? w2[1] : w2[0], send = b2 ? w2[0] : w2[1];
+    x = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  return x;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// glimpse-mask source row for attention row (b, hh): mask.repeat(H,1) indexing (graph_decoder.py:93)
+__device__ __forceinline__ int64_t quirk_row(int64_t b, int hh, long long G) {
+  if (G <= 0) return b;
+  int64_t g0 = (b / G) * G;
+  return g0 + (((b - g0) * NH + hh) % G);
+}
+
+// ---------------------------------------------------------------- wide GEMM: [TM x 128] · [128 x 1024]
+// Xs smem [TM][128]; Wt global [128][1024], streamed in chunks of 16 k-rows x 512 columns (32 KiB).
+// 512 threads = 4 row groups x 128 column threads; each thread owns 8 rows x 4 columns {4tx..4tx+3} of the current
+// 512-column half (conflict-free LDS.128).  epi(m, c, v): row m of the tile, columns c..c+3.
+__device__ __forceinline__ void stage_wide_chunk(const float* __restrict__ Wt, int chunk, float* __restrict__ dst) {
+  const int half = chunk >> 3, k0 = (chunk & 7) * 16;
+  const float* src = Wt + (size_t)k0 * QW + half * 512;
+#pragma unroll
+  for (int i = 0; i < 2048 / NT; ++i) {
+    int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
+    int r = idx >> 7, c4 = idx & 127;
+    cp_async16(dst + r * 512 + c4 * 4, src + (size_t)r * QW + c4 * 4);
+  }
+}
+
+template <class Epi>
+__device__ __forceinline__ void tile_gemm_wide(const float* __restrict__ Xs, const float* __restrict__ Wt,
+                                               float* __restrict__ Wb, Epi epi) {
+  const int tid = threadIdx.x, ty = tid >> 7, tx = tid & 127;
+  stage_wide_chunk(Wt, 0, Wb);
+  cp_async_commit();
+  float acc[8][4];
+  for (int chunk = 0; chunk < 16; ++chunk) {
+    const int half = chunk >> 3, k0 = (chunk & 7) * 16;
+    if ((chunk & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+    if (chunk + 1 < 16) {
+      stage_wide_chunk(Wt, chunk + 1, Wb + ((chunk + 1) & 1) * WCHUNK_FLOATS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* wb = Wb + (chunk & 1) * WCHUNK_FLOATS + tx * 4;
+#pragma unroll
+    for (int kq = 0; kq < 16; kq += 4) {
+      float4 xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty * 8 + i) * E + k0 + kq);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * 512);
+        const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+        }
+      }
+    }
+    __syncthreads();  // the stage may be refilled by the next iteration's cp.async
+    if ((chunk & 7) == 7) {
+      const int c = half * 512 + tx * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) epi(ty * 8 + i, c, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- tall GEMM: [TM x 1024] · [1024 x 128]
+// Cs smem [TM][1024]; Mt global [1024][128] staged with cp.async: chunk kc = rows {kg*256 + kc*16 + r} of the four
+// k-groups (4 x 16 rows x 128 columns = 32 KiB).  512 threads = 4 k-groups x 4 row groups x 32 column threads,
+// 8 rows x 4 columns {4tx..+3} each over a quarter of K; partial sums reduced through `part` (smem, 4*TM*128 floats,
+// may alias Cs).  out[m][e] = sum + bias[e] (bias may be null) is written to smem `out` [TM][128].
+__device__ __forceinline__ void stage_tall_chunk(const float* __restrict__ Mt, int kc, float* __restrict__ dst) {
+#pragma unroll
+  for (int i = 0; i < 2048 / NT; ++i) {
+    int idx = threadIdx.x + NT * i;       // 2048 float4 per chunk
+    int row = idx >> 5, c4 = idx & 31;    // row in [0,64): kg = row >> 4, r = row & 15
+    int k = (row >> 4) * 256 + kc * 16 + (row & 15);
+    cp_async16(dst + row * E + c4 * 4, Mt + (size_t)k * E + c4 * 4);
+  }
+}
+
+__device__ __forceinline__ void tile_gemm_tall(float* __restrict__ Cs, const float* __restrict__ Mt,
+                                               float* __restrict__ Wb, const float* __restrict__ bias,
+                                               float* __restrict__ part, float* __restrict__ out) {
+  const int tid = threadIdx.x, kg = tid >> 7, ty = (tid >> 5) & 3, tx = tid & 31;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  stage_tall_chunk(Mt, 0, Wb);
+  cp_async_commit();
+  for (int kc = 0; kc < 16; ++kc) {
+    if (kc + 1 < 16) {
+      stage_tall_chunk(Mt, kc + 1, Wb + ((kc + 1) & 1) * WCHUNK_FLOATS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* wb = Wb + (kc & 1) * WCHUNK_FLOATS + kg * 16 * E + tx * 4;
+    const int k0 = kg * 256 + kc * 16;
+#pragma unroll
+    for (int kq = 0; kq < 16; kq += 4) {
+      float4 xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(Cs + (ty * 8 + i) * QW + k0 + kq);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + (kq + kk) * E);
+        const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x = kk == 0 ? xv[i].x : (kk == 1 ? xv[i].y : (kk == 2 ? xv[i].z : xv[i].w));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+        }
+      }
+    }
+    __syncthreads();  // also orders the last reads of Cs before `part` (which may alias it) is written
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(part + (kg * TM + ty * 8 + i) * E + tx * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+  for (int o = tid; o < TM * E; o += NT) {
+    float s = part[o] + part[TM * E + o] + part[2 * TM * E + o] + part[3 * TM * E + o];
+    out[o] = s + (bias ? bias[o & (E - 1)] : 0.f);
+  }
+  __syncthreads();
+}
+
+}  // namespace vrpx

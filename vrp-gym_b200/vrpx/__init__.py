@@ -47,8 +47,38 @@ class EncoderWeights(C.Structure):
                 ("depot_w", C.c_void_p), ("depot_b", C.c_void_p), ("layer", EncoderLayer * LAYERS)]
 
 
+class RolloutTrace(C.Structure):
+    _fields_ = [("mask_hist", C.c_void_p), ("load_hist", C.c_void_p), ("qg0", C.c_void_p)]
+
+
 class DecoderWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("ag_t", "af_t", "al_t", "a_c", "a_q0", "a_load", "m_t", "m_c")]
+
+
+class DecoderBwdWeights(C.Structure):
+    _fields_ = [("m_n", C.c_void_p), ("al_n", C.c_void_p)]
+
+
+class DecoderGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dH", "D0", "D1", "Dl", "d_al_t", "d_m_t", "d_m_c")]
+
+
+class EncoderLayerT(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("in_proj_wT", "out_proj_wT", "ff0_wT", "ff2_wT")]
+
+
+class EncoderWeightsT(C.Structure):
+    _fields_ = [("layer", EncoderLayerT * LAYERS)]
+
+
+class EncoderLayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "bn1_w", "bn1_b",
+                                          "ff0_w", "ff0_b", "ff2_w", "ff2_b", "bn2_w", "bn2_b")]
+
+
+class EncoderGrads(C.Structure):
+    _fields_ = [("node_w", C.c_void_p), ("node_b", C.c_void_p), ("depot_w", C.c_void_p), ("depot_b", C.c_void_p),
+                ("layer", EncoderLayerGrads * LAYERS)]
 
 
 _lib = None
@@ -77,11 +107,25 @@ def lib():
     L.vrpx_encoder_workspace_bytes.argtypes = [i64, i32]
     L.vrpx_encoder_workspace_bytes.restype = i64
     L.vrpx_encoder_forward.argtypes = [C.POINTER(EncoderWeights), C.POINTER(EnvView), vp, vp, i64, i32, i32,
-                                       vp, vp, i64, i32, vp]
+                                       vp, vp, i64, i32, vp, vp]
+    L.vrpx_encoder_saved_bytes.argtypes = [i64, i32]
+    L.vrpx_encoder_saved_bytes.restype = i64
+    L.vrpx_encoder_backward_workspace_bytes.argtypes = [i64, i32]
+    L.vrpx_encoder_backward_workspace_bytes.restype = i64
+    L.vrpx_encoder_backward.argtypes = [C.POINTER(EncoderWeights), C.POINTER(EncoderWeightsT), C.POINTER(EnvView), vp, vp,
+                                        i64, i32, vp, vp, C.POINTER(EncoderGrads), vp, i64, i32, vp]
+    L.vrpx_decoder_backward_workspace_bytes.argtypes = [i64, i32]
+    L.vrpx_decoder_backward_workspace_bytes.restype = i64
+    L.vrpx_decoder_backward.argtypes = [C.POINTER(EnvView), C.POINTER(DecoderWeights), C.POINTER(DecoderBwdWeights), vp, vp,
+                                        i32, i64, C.POINTER(RolloutTrace), vp, vp, C.POINTER(DecoderGrads), vp, i64, vp]
+    L.vrpx_gemm_tn_accumulate.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+    L.vrpx_colsum_accumulate.argtypes = [vp, i64, i32, vp, vp]
+    L.vrpx_episode_gather.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    L.vrpx_episode_scatter.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.vrpx_rollout_workspace_bytes.argtypes = [i64, i32]
     L.vrpx_rollout_workspace_bytes.restype = i64
     L.vrpx_rollout.argtypes = [C.POINTER(EnvView), C.POINTER(DecoderWeights), vp, i32, i64, u64, u64, vp, i32, i32,
-                               vp, vp, vp, vp, vp, i64, vp]
+                               vp, vp, vp, vp, C.POINTER(RolloutTrace), vp, i64, vp]
     L.vrpx_debug_gemm.argtypes = [vp, i64, i32, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp]
     if L.vrpx_abi_version() != 1:
         raise VrpxError("libvrpx.so ABI version mismatch")

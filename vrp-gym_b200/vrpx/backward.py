@@ -1,0 +1,145 @@
+"""REINFORCE backward on libvrpx: loss = mean_b(advantage_b * sum_t log p(a_{b,t}))
+(reference agents/graph_tsp_agent.py:179-186 `loss.backward()` through the whole rollout).
+
+No autograd graph is recorded during the fused rollout.  Instead the forward keeps (a) the action tape and the
+per-step masks/loads, (b) the encoder activations; the backward then runs
+  1. vrpx_decoder_backward  — recompute-based backward of every decode step (csrc/decoder_bwd.cu) -> dL/dh and the
+     gradients of the packed decoder arrays,
+  2. the per-episode decoder terms (graph mean, first node, biases) with small GEMM / reduction kernels,
+  3. one torch.autograd pull-back of the packed-array gradients through vrpx.packing.fold_decoder (a handful of
+     128..1024-sized matrix products, float64) to the decoder's own parameters,
+  4. vrpx_encoder_backward — BatchNorm(batch stats) / FF / attention / embedding backward (csrc/encoder_bwd.cu),
+and accumulates into `param.grad` exactly where torch would have put it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+import vrpx
+from vrpx import packing
+
+
+def _acc_grad(p, g):
+    g = g.to(p.dtype)
+    if p.grad is None:
+        p.grad = g.clone()
+    else:
+        p.grad.add_(g)
+
+
+def _gemm_nt(X, W, residual=None, path=0):
+    """Y = X · W^T (+ residual) through the library GEMM (W in [NOUT][K] layout)."""
+    R, K = X.shape
+    NOUT = W.shape[0]
+    Y = torch.empty((R, NOUT), dtype=torch.float32, device=X.device)
+    vrpx.check(vrpx.lib().vrpx_debug_gemm(vrpx.ptr(X), R, K, vrpx.ptr(W), NOUT, None, 0,
+                                          vrpx.ptr(residual) if residual is not None else None, None, None,
+                                          vrpx.ptr(Y), path, vrpx.stream_ptr(X.device)))
+    return Y
+
+
+def decoder_backward(dec, env, h, roll, wts, gemm_path=0):
+    """Back-propagate wts[b] = dL/d(logp_b) through the rollout `roll` (dict from GraphDecoder.rollout_episode with
+    save_for_backward=True).  Accumulates the decoder parameters' .grad and returns dL/dh (B,N,128)."""
+    L = vrpx.lib()
+    dev = h.device
+    st = vrpx.stream_ptr(dev)
+    B, N = env.batch_size, env.num_nodes
+    irp = env._KIND == vrpx.IRP
+    w = dec.packed(irp, dev)
+    tens = dec._packed[irp].tensors
+    sv = roll["saved"]
+    tape = roll["tape"].contiguous()
+    T = int(tape.shape[0])
+    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+    g = {"dH": z(B, N, 128), "D0": z(B, 1024), "D1": z(B, 1024), "Dl": z(B, 1024) if irp else None,
+         "d_al_t": z(128, 1024), "d_m_t": z(1024, 128), "d_m_c": z(128)}
+    gs = vrpx.DecoderGrads(*[None if g[k] is None else g[k].data_ptr() for k in ("dH", "D0", "D1", "Dl", "d_al_t", "d_m_t", "d_m_c")])
+    m_n = tens["m_t"].t().contiguous()
+    al_n = tens["al_t"].t().contiguous()
+    wb = vrpx.DecoderBwdWeights(m_n.data_ptr(), al_n.data_ptr())
+    trace = vrpx.RolloutTrace(sv["mask_hist"].data_ptr(), sv["load_hist"].data_ptr(), sv["qg0"].data_ptr())
+    nbytes = int(L.vrpx_decoder_backward_workspace_bytes(B, N))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    wts = wts.detach().to(dev, torch.float32).contiguous()
+    vrpx.check(L.vrpx_decoder_backward(C.byref(env._view()), C.byref(w), C.byref(wb), vrpx.ptr(h), vrpx.ptr(tape), T,
+                                       int(roll["coupling"]), C.byref(trace), vrpx.ptr(sv["qg"]), vrpx.ptr(wts),
+                                       C.byref(gs), vrpx.ptr(ws), nbytes, st))
+    # ---- per-episode terms: q~ also contains A_g·g + a_c (every step), A_f·h[first] (steps >= 1), a_q0 (step 0)
+    Dsum = g["D0"] + g["D1"]
+    G = torch.empty((B, 128), dtype=torch.float32, device=dev)
+    Xf = None if irp else torch.empty((B, 128), dtype=torch.float32, device=dev)
+    tape0 = tape[0].contiguous()
+    vrpx.check(L.vrpx_episode_gather(vrpx.ptr(h), vrpx.ptr(tape0), B, N, vrpx.ptr(G), vrpx.ptr(Xf) if Xf is not None else None, st))
+    dG = _gemm_nt(Dsum, tens["ag_t"], path=gemm_path)                      # (B,128) = Dsum · A_g
+    dXf = None if irp else _gemm_nt(g["D1"], tens["af_t"], path=gemm_path)  # (B,128) = D1 · A_f
+    vrpx.check(L.vrpx_episode_scatter(vrpx.ptr(g["dH"]), vrpx.ptr(tape0), B, N, vrpx.ptr(dG),
+                                      vrpx.ptr(dXf) if dXf is not None else None, st))
+    grads = {"al_t": g["d_al_t"], "m_t": g["d_m_t"], "m_c": g["d_m_c"], "ag_t": z(128, 1024), "a_c": z(1024), "a_q0": z(1024)}
+    vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(G), vrpx.ptr(Dsum), vrpx.ptr(grads["ag_t"]), B, 128, 1024, st))
+    vrpx.check(L.vrpx_colsum_accumulate(vrpx.ptr(Dsum), B, 1024, vrpx.ptr(grads["a_c"]), st))
+    vrpx.check(L.vrpx_colsum_accumulate(vrpx.ptr(g["D0"]), B, 1024, vrpx.ptr(grads["a_q0"]), st))
+    if irp:
+        grads["a_load"] = z(1024)
+        vrpx.check(L.vrpx_colsum_accumulate(vrpx.ptr(g["Dl"]), B, 1024, vrpx.ptr(grads["a_load"]), st))
+    else:
+        grads["af_t"] = z(128, 1024)
+        vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(Xf), vrpx.ptr(g["D1"]), vrpx.ptr(grads["af_t"]), B, 128, 1024, st))
+    # ---- pull the packed-array gradients back to the module parameters (tiny weight-only products)
+    params = [p for p in dec.parameters() if p.requires_grad]
+    with torch.enable_grad():
+        folded = packing.fold_decoder(dec, irp)
+        outs, gouts = [], []
+        for k, gv in grads.items():
+            if folded.get(k) is not None:
+                outs.append(folded[k])
+                gouts.append(gv.double())
+        pg = torch.autograd.grad(outs, params, gouts, allow_unused=True)
+    for p, gp in zip(params, pg):
+        if gp is not None:
+            _acc_grad(p, gp)
+    return g["dH"]
+
+
+def encoder_backward(enc, env, depot, saved, dH, gemm_path=0):
+    """Back-propagate dL/dh (overwritten) through the train-mode encoder; accumulates the parameters' .grad."""
+    L = vrpx.lib()
+    dev = dH.device
+    B, N = env.batch_size, env.num_nodes
+    w = packing.encoder_struct(enc, dev)
+    keep = []
+    wt = vrpx.EncoderWeightsT()
+    gr = vrpx.EncoderGrads()
+
+    def gp(p):
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        assert p.grad.is_contiguous()
+        return p.grad.data_ptr()
+
+    gr.node_w, gr.node_b = gp(enc.node_embed.weight), gp(enc.node_embed.bias)
+    dep = getattr(enc, "depot_embed", None)
+    gr.depot_w = gp(dep.weight) if dep is not None else None
+    gr.depot_b = gp(dep.bias) if dep is not None else None
+    for i, layer in enumerate(enc.attention_layers):
+        a = layer.attention_layer
+        tr = [a.in_proj_weight.detach().t().contiguous(), a.out_proj.weight.detach().t().contiguous(),
+              layer.ff[0].weight.detach().t().contiguous(), layer.ff[2].weight.detach().t().contiguous()]
+        keep.extend(tr)
+        T_ = wt.layer[i]
+        T_.in_proj_wT, T_.out_proj_wT, T_.ff0_wT, T_.ff2_wT = [t.data_ptr() for t in tr]
+        G_ = gr.layer[i]
+        G_.in_proj_w, G_.in_proj_b = gp(a.in_proj_weight), gp(a.in_proj_bias)
+        G_.out_proj_w, G_.out_proj_b = gp(a.out_proj.weight), gp(a.out_proj.bias)
+        G_.bn1_w, G_.bn1_b = gp(layer.bn1.norm.weight), gp(layer.bn1.norm.bias)
+        G_.ff0_w, G_.ff0_b = gp(layer.ff[0].weight), gp(layer.ff[0].bias)
+        G_.ff2_w, G_.ff2_b = gp(layer.ff[2].weight), gp(layer.ff[2].bias)
+        G_.bn2_w, G_.bn2_b = gp(layer.bn2.norm.weight), gp(layer.bn2.norm.bias)
+    nbytes = int(L.vrpx_encoder_backward_workspace_bytes(B, N))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    vrpx.check(L.vrpx_encoder_backward(C.byref(w), C.byref(wt), C.byref(env._view()), None,
+                                       vrpx.ptr(depot) if depot is not None else None, B, N, vrpx.ptr(saved),
+                                       vrpx.ptr(dH), C.byref(gr), vrpx.ptr(ws), nbytes, gemm_path, vrpx.stream_ptr(dev)))
+    return dH
