@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--gemm-path", type=int, default=0, help="0 tcgen05 3xTF32, 1 fp32 SIMT")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=69)
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "train"],
+                    help="rollout: greedy evaluate (headline); train: one REINFORCE step (sampled rollout + sampled "
+                         "baseline rollout + backward + Adam), BASELINE.json configs[3]")
     return ap.parse_args()
 
 
@@ -140,6 +143,66 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------ train step
+def run_train_bench(a, Env, Agent, dev, rank, world, dist):
+    """One step = the body of TSPAgent.train's epoch without baseline_update (graph_tsp_agent.py:176-186): reset,
+    sampled rollout with grad (train-mode BatchNorm), sampled baseline rollout, REINFORCE loss, backward, Adam."""
+    import vrpx
+
+    B, N = a.batch, a.nodes
+    agent = Agent(seed=a.seed)
+    agent.model.encoder.gemm_path = agent.target_model.encoder.gemm_path = a.gemm_path
+    env = Env(N, B, 0, seed=a.seed, instance_rng="philox", instance_offset=rank * B)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def one():
+        agent.model.train()
+        loss_m, loss_b, logp = agent.step(env, (False, True))
+        adv = (loss_m - loss_b) * -1
+        loss = agent.policy_gradient_step(adv, logp)
+        return env.step_count, float(loss)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    for _ in range(max(a.warmup, 3)):
+        T, loss = one()
+    barrier()
+    l0 = vrpx.launch_count()
+    e0, e1 = ev(), ev()
+    w0 = time.perf_counter()
+    e0.record()
+    inst_steps = 0
+    for _ in range(a.steps):
+        T, loss = one()
+        inst_steps += 2 * T * B
+    e1.record()
+    barrier()
+    w1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tot = torch.tensor([float(inst_steps)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms, inst_steps = float(t.item()), float(tot.item())
+        line = {"metric": "train_instance_steps_per_sec", "value": inst_steps / (ms * 1e-3), "unit": "instance-steps/s",
+                "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"REINFORCE train step {a.kind.upper()}-{N}: sampled rollout + sampled baseline rollout "
+                                       f"+ backward + Adam, {B} instances per GPU", "instances_per_gpu": B, "nodes": N},
+                "loss": loss, "clocks": clocks.stop(w0, w1), "gpu_launches": int(vrpx.launch_count() - l0),
+                "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     a = parse()
@@ -166,6 +229,8 @@ def main():
     Env = {"tsp": TSPEnv, "vrp": VRPEnv, "irp": IRPEnv}[a.kind]
     Agent = {"tsp": TSPAgent, "vrp": VRPAgent, "irp": IRPAgent}[a.kind]
     B, N = a.batch, a.nodes
+    if a.mode == "train":
+        return run_train_bench(a, Env, Agent, dev, rank, world, dist)
     agent = Agent(seed=a.seed)  # identical seed-initialised weights on every rank (no checkpoint in the reference tree)
     model = agent.model
     model.eval()

@@ -146,8 +146,26 @@ class TSPAgent:
         self.opt.zero_grad()
         # d loss / d log_prob_b = advantage_b / B; the gradient flows only through log_prob (advantage is data)
         self.model.backward(advantage.detach() / B)
+        self._allreduce_gradients()
         self.opt.step()
         return loss
+
+    def _allreduce_gradients(self):
+        """Data-parallel training: every rank holds a shard of the batch (its own reference batch); the gradient of
+        the global mean loss is the mean over ranks of the local gradients — one flat NCCL all-reduce."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        from vrpx import sharding
+
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        sharding.allreduce_mean_(flat)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
 
     def save_model(self, episode: int, check_point_dir: str) -> None:
         if not os.path.exists(check_point_dir):
@@ -168,8 +186,16 @@ class TSPAgent:
                 baseline_model_cost.append(loss_b)
         current_model_cost = torch.cat(current_model_cost)
         baseline_model_cost = torch.cat(baseline_model_cost)
-        advantage = ((current_model_cost - baseline_model_cost) * -1).mean()
-        _, p_value = stats.ttest_rel(current_model_cost.tolist(), baseline_model_cost.tolist())
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from vrpx import sharding  # same decision on every rank from 3 all-reduced doubles
+
+            mean_d, p_value = sharding.paired_ttest_allreduce(-current_model_cost, -baseline_model_cost)
+            advantage = torch.tensor(mean_d)
+        else:
+            advantage = ((current_model_cost - baseline_model_cost) * -1).mean()
+            _, p_value = stats.ttest_rel(current_model_cost.tolist(), baseline_model_cost.tolist())
         if advantage.item() <= 0 and p_value <= 0.05:
             print("replacing baceline")
             self.target_model.load_state_dict(self.model.state_dict())
