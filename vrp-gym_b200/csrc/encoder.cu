@@ -296,7 +296,7 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
               (long long)ws_bytes, (long long)vrpx_encoder_workspace_bytes(B, N));
     return VRPX_ERR_ARG;
   }
-  auto gemm = gemm_path == 0 ? gemm_tc : gemm_simt;
+  auto gemm = [gemm_path](const GemmArgs& ga, cudaStream_t st) { return gemm_dispatch(gemm_path, ga, st); };
   BnSlots* slots = reinterpret_cast<BnSlots*>(ws);
   float* big = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kSmallWs);
   int attn_smem = 2 * NH * N * 16 * (int)sizeof(float);

@@ -219,7 +219,7 @@ int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_encoder_weig
   VRPX_CHECK_ARG(x || (env && env->xy && (w->f == 2 || env->demand)), "need x or an env with features");
   VRPX_CHECK_ARG(ws_bytes >= vrpx_encoder_backward_workspace_bytes(B, N), "workspace too small");
   const int64_t R = B * N;
-  auto gemm = gemm_path == 0 ? gemm_tc : gemm_simt;
+  auto gemm = [gemm_path](const GemmArgs& ga, cudaStream_t st) { return gemm_dispatch(gemm_path, ga, st); };
   BnBwdSlot* slots = reinterpret_cast<BnBwdSlot*>(ws);
   float* embC = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 12288);  // 2 x [128][4]
   float* T512 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kBwdSmall);

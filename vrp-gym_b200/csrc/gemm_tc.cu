@@ -1,4 +1,5 @@
-// gemm_tc.cu — fp32-accurate GEMM on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in
+// gemm_tc.cu — first-generation (non-persistent, thread-staged) tcgen05 GEMM, kept as cross-check path 2; the
+// production path is gemm_tc2.cu.  fp32-accurate GEMM on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in
 // TMEM) for the encoder's dense layers (agents/graph_encoder.py:170-181: in_proj / out_proj / FF).
 //
 // Precision policy: the spec asks <= 1e-5 relative on logits, single-pass TF32 gives ~1e-3.  Each fp32
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tc(GemmArgs a) {
 
 }  // namespace tc
 
-int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
+int gemm_tc_v1(const GemmArgs& a, cudaStream_t stream) {
   if (a.K % tc::BK != 0 || a.NOUT % tc::BN != 0 || a.R <= 0) {
     set_error("gemm_tc: unsupported shape R=%lld K=%d NOUT=%d", (long long)a.R, a.K, a.NOUT);
     return VRPX_ERR_ARG;
@@ -222,5 +223,7 @@ extern "C" int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float
                                const float* bias, int32_t relu, const float* residual, const float* scale,
                                const float* shift, float* Y, int32_t path, void* stream) {
   vrpx::GemmArgs g{X, R, K, W, NOUT, bias, relu, residual, scale, shift, Y};
-  return path == 0 ? vrpx::gemm_tc(g, (cudaStream_t)stream) : vrpx::gemm_simt(g, (cudaStream_t)stream);
+  if (path == 0) return vrpx::gemm_tc(g, (cudaStream_t)stream);
+  if (path == 2) return vrpx::gemm_tc_v1(g, (cudaStream_t)stream);
+  return vrpx::gemm_simt(g, (cudaStream_t)stream);
 }
