@@ -41,14 +41,14 @@ struct RolloutParams {
   int* notdone;       // [Tmax + 1]
 };
 
-constexpr size_t SMEM_TOTAL = SMEM_X + SMEM_QC + SMEM_W;
+constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_MMA;   // 16.5 + 128.5 + 68 KiB
 
 // ---------------------------------------------------------------- the persistent kernel
 __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Xs = reinterpret_cast<float*>(smem_raw);
-  float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X);
-  float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X + SMEM_QC);
+  float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA);
+  float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA + SMEM_QC_MMA);
   __shared__ float s_loadf[TM];
   __shared__ int s_anyleft;
 
@@ -74,15 +74,15 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         float inv = 1.0f / (float)N;
         g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
       }
-      *reinterpret_cast<float4*>(Xs + m * E + lane * 4) = g;
+      *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = g;
     }
     __syncthreads();
-    tile_gemm_wide(Xs, p.w.ag_t, Wb, [&](int m, int c, float4 v) {   // Q~g = A_g · g + a_c
+    tile_gemm_wide_mma(Xs, p.w.ag_t, Wb, [&](int m, int c, float v0, float v1) {   // Q~g = A_g · g + a_c
       if (m >= cnt) return;
-      const float4 ac = *reinterpret_cast<const float4*>(p.w.a_c + c);
-      v = make_float4(v.x + ac.x, v.y + ac.y, v.z + ac.z, v.w + ac.w);
-      *reinterpret_cast<float4*>(p.qg + (base + m) * QW + c) = v;
-      if (p.qg0) *reinterpret_cast<float4*>(p.qg0 + (base + m) * QW + c) = v;
+      const float2 ac = *reinterpret_cast<const float2*>(p.w.a_c + c);
+      const float2 v = make_float2(v0 + ac.x, v1 + ac.y);
+      *reinterpret_cast<float2*>(p.qg + (base + m) * QW + c) = v;
+      if (p.qg0) *reinterpret_cast<float2*>(p.qg0 + (base + m) * QW + c) = v;
     });
     __syncthreads();
   }
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           int last = p.env.cur[base + m];
           xv = __ldg(reinterpret_cast<const float4*>(h + ((base + m) * N + last) * E) + lane);
         }
-        *reinterpret_cast<float4*>(Xs + m * E + lane * 4) = xv;
+        *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = xv;
         const float lf = (m < cnt) ? (float)p.env.load[base + m] : 0.f;
         if (lane == 0) s_loadf[m] = lf;
         if (m < cnt && p.mask_hist && lane < 4)
@@ -116,28 +116,28 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           int m = o >> 10, c = o & (QW - 1);
           float y = p.qg[(base + m) * QW + c] + p.w.a_q0[c];
           if (kind == VRPX_IRP) y = fmaf(s_loadf[m], p.w.a_load[c], y);
-          QC[o] = y;
+          QC[m * QC_LD + c] = y;
         }
       } else {
         if (t == 1 && kind != VRPX_IRP) {
-          tile_gemm_wide(Xs, p.w.af_t, Wb, [&](int m, int c, float4 v) {   // fold `first` (graph_decoder.py:111-113)
+          tile_gemm_wide_mma(Xs, p.w.af_t, Wb, [&](int m, int c, float v0, float v1) {   // fold `first` (graph_decoder.py:111-113)
             if (m >= cnt) return;
-            float4* qgp = reinterpret_cast<float4*>(p.qg + (base + m) * QW + c);
-            const float4 q = *qgp;
-            *qgp = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
+            float2* qgp = reinterpret_cast<float2*>(p.qg + (base + m) * QW + c);
+            const float2 q = *qgp;
+            *qgp = make_float2(q.x + v0, q.y + v1);
           });
           __syncthreads();  // qg updates are re-read by other threads' epilogue below? (same thread) — keep ordering explicit
         }
-        tile_gemm_wide(Xs, p.w.al_t, Wb, [&](int m, int c, float4 v) {   // q~ = A_l · h[last] + Q~g (+ load · a_load)
+        tile_gemm_wide_mma(Xs, p.w.al_t, Wb, [&](int m, int c, float v0, float v1) {   // q~ = A_l · h[last] + Q~g (+ load · a_load)
           if (m >= cnt) return;
-          const float4 q = *reinterpret_cast<const float4*>(p.qg + (base + m) * QW + c);
-          v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+          const float2 q = *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c);
+          float2 v = make_float2(v0 + q.x, v1 + q.y);
           if (kind == VRPX_IRP) {
-            const float4 al = *reinterpret_cast<const float4*>(p.w.a_load + c);
+            const float2 al = *reinterpret_cast<const float2*>(p.w.a_load + c);
             const float lf = s_loadf[m];
-            v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
+            v = make_float2(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y));
           }
-          *reinterpret_cast<float4*>(QC + m * QW + c) = v;
+          *reinterpret_cast<float2*>(QC + m * QC_LD + c) = v;
         });
       }
       __syncthreads();
@@ -145,45 +145,66 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       // ---------------- P2: glimpse attention, one warp per instance
       for (int m = warp; m < cnt; m += NT / 32) {
         const int64_t b = base + m;
-        float* slot = QC + m * QW;
-        float4 qt[NH];
+        float* slot = QC + m * QC_LD;
+        // ---- pass 1 on the tensor pipe: S[node][head] = H_b[node][:] · q~[head][:]  (m16n8k8, M = 16 nodes, N = 8 heads)
+        // Fragment coordinates g = lane >> 2, t = lane & 3.  The K (embedding) axis is permuted so that every thread
+        // streams whole float4 chunks: chunk c (0..7) of thread t covers dims 16c + 4t + {0,1,2,3}; k-step 2c + u uses
+        // mma k-index t <-> dim 16c+4t+2u and k-index t+4 <-> dim 16c+4t+2u+1, for A (node rows) and B (q~) alike.
+        const int g = lane >> 2, t = lane & 3;
+        float4 qv[8];   // q~[head g][dims of this thread]
 #pragma unroll
-        for (int hh = 0; hh < NH; ++hh) qt[hh] = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
+        for (int c = 0; c < 8; ++c) qv[c] = *reinterpret_cast<const float4*>(slot + g * E + 16 * c + 4 * t);
         __syncwarp();
-        // this lane's head (lane >> 2) & 7 reads the mask of instance quirk_row(b, head)
-        const int myh = (lane >> 2) & 7;
-        const uint32_t* nbm = p.env.mask + quirk_row(b, myh, p.G) * 4;
-        uint32_t nb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) nb[i] = __ldcg(nbm + i);
-        const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
-        // pass 1: scores[hh][n]; rows are fetched four at a time, one batch ahead of their use
+        // masks of the instances whose rows the reference adds to heads 2t and 2t+1 (mask.repeat(H,1), graph_decoder.py:93)
+        uint32_t nb0[4], nb1[4];
         {
-          float4 nxt[4];
+          const uint32_t* m0 = p.env.mask + quirk_row(b, 2 * t, p.G) * 4;
+          const uint32_t* m1 = p.env.mask + quirk_row(b, 2 * t + 1, p.G) * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) nxt[i] = (i < N) ? __ldg(hp + i * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int n0 = 0; n0 < N; n0 += 4) {
-            float4 hv4[4];
+          for (int i = 0; i < 4; ++i) { nb0[i] = __ldcg(m0 + i); nb1[i] = __ldcg(m1 + i); }
+        }
+        const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
+        for (int n0 = 0; n0 < N; n0 += 16) {
+          const int na = n0 + g, nbb = n0 + g + 8;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hv4[i] = nxt[i];
+          for (int half = 0; half < 2; ++half) {
+            float4 va[4], vb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = n0 + 4 + i;
-              if (n < N) nxt[i] = __ldg(hp + n * (E / 4));
+            for (int cc = 0; cc < 4; ++cc) {
+              const int c = half * 4 + cc;
+              va[cc] = (na < N) ? __ldg(hrow + na * (E / 4) + 4 * c + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+              vb[cc] = (nbb < N) ? __ldg(hrow + nbb * (E / 4) + 4 * c + t) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = n0 + i;
-              if (n < N) {
-                const float4 hv = hv4[i];
-                float v[NH];
+            for (int cc = 0; cc < 4; ++cc) {
+              const int c = half * 4 + cc;
+              const float ae[4] = {va[cc].x, va[cc].y, va[cc].z, va[cc].w};
+              const float be[4] = {vb[cc].x, vb[cc].y, vb[cc].z, vb[cc].w};
+              const float qe[4] = {qv[c].x, qv[c].y, qv[c].z, qv[c].w};
 #pragma unroll
-                for (int hh = 0; hh < NH; ++hh)
-                  v[hh] = fmaf(qt[hh].x, hv.x, fmaf(qt[hh].y, hv.y, fmaf(qt[hh].z, hv.z, qt[hh].w * hv.w)));
-                float sc = reduce8(v, lane);
-                if ((lane & 3) == 0) slot[myh * E + n] = sc + (float)((nb[n >> 5] >> (n & 31)) & 1u);
+              for (int u = 0; u < 2; ++u) {
+                uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+                split_tf32(ae[2 * u], ah[0], al[0]);       // (row g,   k = t)
+                split_tf32(be[2 * u], ah[1], al[1]);       // (row g+8, k = t)
+                split_tf32(ae[2 * u + 1], ah[2], al[2]);   // (row g,   k = t+4)
+                split_tf32(be[2 * u + 1], ah[3], al[3]);   // (row g+8, k = t+4)
+                split_tf32(qe[2 * u], bh0, bl0);           // (k = t,   n = g)
+                split_tf32(qe[2 * u + 1], bh1, bl1);       // (k = t+4, n = g)
+                mma_tf32_16x8x8(acc, al, bh0, bh1);
+                mma_tf32_16x8x8(acc, ah, bl0, bl1);
+                mma_tf32_16x8x8(acc, ah, bh0, bh1);
               }
             }
+          }
+          // C fragment: acc[0], acc[1] = node na, heads 2t, 2t+1;  acc[2], acc[3] = node nbb
+          if (na < N) {
+            slot[(2 * t) * E + na] = acc[0] + (float)((nb0[na >> 5] >> (na & 31)) & 1u);
+            slot[(2 * t + 1) * E + na] = acc[1] + (float)((nb1[na >> 5] >> (na & 31)) & 1u);
+          }
+          if (nbb < N) {
+            slot[(2 * t) * E + nbb] = acc[2] + (float)((nb0[nbb >> 5] >> (nbb & 31)) & 1u);
+            slot[(2 * t + 1) * E + nbb] = acc[3] + (float)((nb1[nbb >> 5] >> (nbb & 31)) & 1u);
           }
         }
         __syncwarp();
@@ -222,59 +243,67 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           }
         }
         __syncwarp();
-        // pass 2: c[hh][4 dims of this lane]
-        float4 c[NH];
+        // ---- pass 2 on the tensor pipe: c[head][dim] = sum_n P[n][head] h_n[dim]  (M = 16 dims, N = 8 heads, K = 8 nodes)
+        // Thread g streams the float4 chunks 8c' + g (dims 32c' + 4g + e) of node rows n0+t and n0+t+4; m-tile
+        // j = 2c' + u has row g <-> dim 32c'+4g+2u and row g+8 <-> dim 32c'+4g+2u+1.  B = P[n][head] from the slot.
+        float cacc[8][4];
 #pragma unroll
-        for (int hh = 0; hh < NH; ++hh) c[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
-        {
-          float4 nxt[4];
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) nxt[i] = (i < N) ? __ldg(hp + i * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int n0 = 0; n0 < N; n0 += 4) {
-            float4 hv4[4];
+          for (int i = 0; i < 4; ++i) cacc[j][i] = 0.f;
+        for (int n0 = 0; n0 < N; n0 += 8) {
+          const int na = n0 + t, nbb = n0 + t + 4;
+          float4 va[4], vb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hv4[i] = nxt[i];
+          for (int cq = 0; cq < 4; ++cq) {
+            va[cq] = (na < N) ? __ldg(hrow + na * (E / 4) + 8 * cq + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[cq] = (nbb < N) ? __ldg(hrow + nbb * (E / 4) + 8 * cq + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32((na < N) ? slot[na * 8 + g] : 0.f, bh0, bl0);      // (k = t,   n = head g)
+          split_tf32((nbb < N) ? slot[nbb * 8 + g] : 0.f, bh1, bl1);    // (k = t+4, n = head g)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = n0 + 4 + i;
-              if (n < N) nxt[i] = __ldg(hp + n * (E / 4));
-            }
+          for (int cq = 0; cq < 4; ++cq) {
+            const float ae[4] = {va[cq].x, va[cq].y, va[cq].z, va[cq].w};
+            const float be[4] = {vb[cq].x, vb[cq].y, vb[cq].z, vb[cq].w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = n0 + i;
-              if (n < N) {
-                const float4 hv = hv4[i];
-                const float4 p0 = *reinterpret_cast<const float4*>(slot + n * 8);
-                const float4 p1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
-                const float pv[NH] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-                for (int hh = 0; hh < NH; ++hh) {
-                  c[hh].x = fmaf(pv[hh], hv.x, c[hh].x);
-                  c[hh].y = fmaf(pv[hh], hv.y, c[hh].y);
-                  c[hh].z = fmaf(pv[hh], hv.z, c[hh].z);
-                  c[hh].w = fmaf(pv[hh], hv.w, c[hh].w);
-                }
-              }
+            for (int u = 0; u < 2; ++u) {
+              uint32_t ah[4], al[4];
+              split_tf32(ae[2 * u], ah[0], al[0]);       // (row g   = dim 32cq+4g+2u,   k = t   = node na)
+              split_tf32(ae[2 * u + 1], ah[1], al[1]);   // (row g+8 = dim 32cq+4g+2u+1, k = t)
+              split_tf32(be[2 * u], ah[2], al[2]);       // (row g,   k = t+4 = node nbb)
+              split_tf32(be[2 * u + 1], ah[3], al[3]);   // (row g+8, k = t+4)
+              mma_tf32_16x8x8(cacc[2 * cq + u], al, bh0, bh1);
+              mma_tf32_16x8x8(cacc[2 * cq + u], ah, bl0, bl1);
+              mma_tf32_16x8x8(cacc[2 * cq + u], ah, bh0, bh1);
             }
           }
         }
-        __syncwarp();
+        __syncwarp();  // every lane is done reading P before c overwrites the slot
+        // C fragment of m-tile j = 2cq+u: [0] (dim d, head 2t), [1] (dim d, head 2t+1), [2] (dim d+1, head 2t),
+        // [3] (dim d+1, head 2t+1) with d = 32cq + 4g + 2u  ->  c[head][dim] for GEMM-B
 #pragma unroll
-        for (int hh = 0; hh < NH; ++hh) *reinterpret_cast<float4*>(slot + hh * E + lane * 4) = c[hh];
+        for (int cq = 0; cq < 4; ++cq)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int d = 32 * cq + 4 * g + 2 * u, j = 2 * cq + u;
+            *reinterpret_cast<float2*>(slot + (2 * t) * E + d) = make_float2(cacc[j][0], cacc[j][2]);
+            *reinterpret_cast<float2*>(slot + (2 * t + 1) * E + d) = make_float2(cacc[j][1], cacc[j][3]);
+          }
       }
       // rows >= cnt of C must be finite for GEMM-B (results unused): zero them
-      for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[o] = 0.f;
+      for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[(o >> 10) * QC_LD + (o & (QW - 1))] = 0.f;
       __syncthreads();
 
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
-      tile_gemm_tall(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs);
+      tile_gemm_tall_mma(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
 
       // ---------------- P4: logits, action, environment transition
       bool unfinished = false;
       for (int m = warp; m < cnt; m += NT / 32) {
         const int64_t b = base + m;
-        float* slot = QC + m * QW;  // free scratch again
-        const float4 qh = *reinterpret_cast<const float4*>(Xs + m * E + lane * 4);
+        float* slot = QC + m * QC_LD;  // free scratch again
+        const float4 qh = *reinterpret_cast<const float4*>(Xs + m * XS_LD + lane * 4);
         const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
         {
           float4 nxt[8];

@@ -207,4 +207,177 @@ __device__ __forceinline__ void tile_gemm_tall(float* __restrict__ Cs, const flo
   __syncthreads();
 }
 
+// ================================================================ tensor-pipe variants (rollout kernel)
+// The same two tile GEMMs on the legacy warp-level tensor path: mma.sync.m16n8k8 TF32 with the 3-term split
+// (acc += Alo·Bhi + Ahi·Blo + Ahi·Bhi, ~fp32 accuracy).  Measured on B200 (tools/mma_bench.cu): 480 MAC/clk/SM for
+// mma.sync TF32 vs 123 MAC/clk/SM for FFMA, and the tensor pipe runs beside the FMA pipe.  tcgen05 needs M >= 64
+// rows per instruction and operands in the UMMA smem layout; a 32-instance tile whose 1024-wide result must stay in
+// shared memory for the per-instance phases does not fit that shape, so these tile GEMMs use register fragments.
+// Shared-memory leading dimensions are padded so that fragment loads are bank-conflict free:
+constexpr int XS_LD = E + 4;        // 132: A fragments (row g, col t): bank (4g + t) % 32
+constexpr int QC_LD = QW + 4;       // 1028
+constexpr int WIDE_LD = QW + 8;     // 1032: B fragments (k = t, n = g): bank (8t + g) % 32
+constexpr int TALL_LD = E + 8;      // 136
+constexpr int WIDE_CHUNK_FLOATS = 8 * WIDE_LD;    // one mma k-step (8 k-rows) of all 1024 columns, 33 KiB
+constexpr int TALL_CHUNK_FLOATS = 64 * TALL_LD;   // 8 k-groups x 8 k-rows x 128 columns, 34.8 KiB
+constexpr size_t SMEM_X_MMA = (size_t)TM * XS_LD * sizeof(float);
+constexpr size_t SMEM_QC_MMA = (size_t)TM * QC_LD * sizeof(float);
+constexpr size_t SMEM_W_MMA = 2 * (size_t)TALL_CHUNK_FLOATS * sizeof(float);
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A fragments (hi and lo) of the two 16-row tiles for one k-step, from a row-major smem matrix with leading dim ld.
+__device__ __forceinline__ void load_a_frags(const float* __restrict__ A, int ld, int k0, int g, int t,
+                                             uint32_t (&ah)[2][4], uint32_t (&al)[2][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const float* r0 = A + (mt * 16 + g) * ld + k0 + t;
+    const float* r1 = r0 + 8 * ld;
+    split_tf32(r0[0], ah[mt][0], al[mt][0]);
+    split_tf32(r1[0], ah[mt][1], al[mt][1]);
+    split_tf32(r0[4], ah[mt][2], al[mt][2]);
+    split_tf32(r1[4], ah[mt][3], al[mt][3]);
+  }
+}
+
+__device__ __forceinline__ void stage_wide_chunk_mma(const float* __restrict__ Wt, int kstep, float* __restrict__ dst) {
+  const float* src = Wt + (size_t)kstep * 8 * QW;
+#pragma unroll
+  for (int i = 0; i < 2048 / NT; ++i) {
+    int idx = threadIdx.x + NT * i;       // 8 rows x 256 float4
+    int r = idx >> 8, c4 = idx & 255;
+    cp_async16(dst + r * WIDE_LD + c4 * 4, src + (size_t)r * QW + c4 * 4);
+  }
+}
+
+// out[32][1024] = Xs[32][128] (ld XS_LD) · Wt[128][1024].  Warp w owns columns [64w, 64w + 64).
+// epi(m, c, v0, v1): row m, columns c and c+1.
+template <class Epi>
+__device__ __forceinline__ void tile_gemm_wide_mma(const float* __restrict__ Xs, const float* __restrict__ Wt,
+                                                   float* __restrict__ Wb, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+  stage_wide_chunk_mma(Wt, 0, Wb);
+  cp_async_commit();
+  for (int ks = 0; ks < 16; ++ks) {
+    if (ks + 1 < 16) {
+      stage_wide_chunk_mma(Wt, ks + 1, Wb + ((ks + 1) & 1) * TALL_CHUNK_FLOATS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    uint32_t ah[2][4], al[2][4];
+    load_a_frags(Xs, XS_LD, ks * 8, g, t, ah, al);
+    const float* wb = Wb + (ks & 1) * TALL_CHUNK_FLOATS + warp * 64 + g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t bh0, bl0, bh1, bl1;
+      split_tf32(wb[t * WIDE_LD + 8 * j], bh0, bl0);
+      split_tf32(wb[(t + 4) * WIDE_LD + 8 * j], bh1, bl1);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_tf32_16x8x8(acc[mt][j], al[mt], bh0, bh1);
+        mma_tf32_16x8x8(acc[mt][j], ah[mt], bl0, bl1);
+        mma_tf32_16x8x8(acc[mt][j], ah[mt], bh0, bh1);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = warp * 64 + 8 * j + 2 * t;
+      epi(mt * 16 + g, c, acc[mt][j][0], acc[mt][j][1]);
+      epi(mt * 16 + g + 8, c, acc[mt][j][2], acc[mt][j][3]);
+    }
+}
+
+__device__ __forceinline__ void stage_tall_chunk_mma(const float* __restrict__ Mt, int kc, float* __restrict__ dst) {
+#pragma unroll
+  for (int i = 0; i < 2048 / NT; ++i) {
+    int idx = threadIdx.x + NT * i;       // 64 rows x 32 float4
+    int row = idx >> 5, c4 = idx & 31;    // row = kg * 8 + r
+    int k = (row >> 3) * 128 + kc * 8 + (row & 7);
+    cp_async16(dst + row * TALL_LD + c4 * 4, Mt + (size_t)k * E + c4 * 4);
+  }
+}
+
+// out[32][128] (ld out_ld) = Cs[32][1024] (ld QC_LD) · Mt[1024][128] + bias.  Warp (kg = w >> 1, ng = w & 1) owns
+// columns [64 ng, 64 ng + 64) over the k range [128 kg, 128 kg + 128); the 8 partial sums go through `part`
+// ([8][32][128] floats, may alias Cs).
+__device__ __forceinline__ void tile_gemm_tall_mma(float* __restrict__ Cs, const float* __restrict__ Mt,
+                                                   float* __restrict__ Wb, const float* __restrict__ bias,
+                                                   float* __restrict__ part, float* __restrict__ out, int out_ld) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int kg = warp >> 1, ng = warp & 1;
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+  stage_tall_chunk_mma(Mt, 0, Wb);
+  cp_async_commit();
+  for (int kc = 0; kc < 16; ++kc) {
+    if (kc + 1 < 16) {
+      stage_tall_chunk_mma(Mt, kc + 1, Wb + ((kc + 1) & 1) * TALL_CHUNK_FLOATS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    uint32_t ah[2][4], al[2][4];
+    load_a_frags(Cs, QC_LD, kg * 128 + kc * 8, g, t, ah, al);
+    const float* wb = Wb + (kc & 1) * TALL_CHUNK_FLOATS + kg * 8 * TALL_LD + ng * 64 + g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t bh0, bl0, bh1, bl1;
+      split_tf32(wb[t * TALL_LD + 8 * j], bh0, bl0);
+      split_tf32(wb[(t + 4) * TALL_LD + 8 * j], bh1, bl1);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_tf32_16x8x8(acc[mt][j], al[mt], bh0, bh1);
+        mma_tf32_16x8x8(acc[mt][j], ah[mt], bl0, bl1);
+        mma_tf32_16x8x8(acc[mt][j], ah[mt], bh0, bh1);
+      }
+    }
+    __syncthreads();  // also orders the last reads of Cs before `part` (which may alias it) is written
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ng * 64 + 8 * j + 2 * t;
+      *reinterpret_cast<float2*>(part + (kg * TM + mt * 16 + g) * E + c) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+      *reinterpret_cast<float2*>(part + (kg * TM + mt * 16 + g + 8) * E + c) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+    }
+  __syncthreads();
+  for (int o = tid; o < TM * E; o += NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k * TM * E + o];
+    out[(o >> 7) * out_ld + (o & (E - 1))] = s + (bias ? bias[o & (E - 1)] : 0.f);
+  }
+  __syncthreads();
+}
+
 }  // namespace vrpx
