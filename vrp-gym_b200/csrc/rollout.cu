@@ -41,7 +41,7 @@ struct RolloutParams {
   int* notdone;       // [Tmax + 1]
 };
 
-constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_MMA;   // 16.5 + 128.5 + 68 KiB
+constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_MMA;   // 16.5 + 128.5 + 72 KiB
 
 // ---------------------------------------------------------------- the persistent kernel
 __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
@@ -77,13 +77,14 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = g;
     }
     __syncthreads();
-    tile_gemm_wide_mma(Xs, p.w.ag_t, Wb, [&](int m, int c, float v0, float v1) {   // Q~g = A_g · g + a_c
-      if (m >= cnt) return;
-      const float2 ac = *reinterpret_cast<const float2*>(p.w.a_c + c);
-      const float2 v = make_float2(v0 + ac.x, v1 + ac.y);
-      *reinterpret_cast<float2*>(p.qg + (base + m) * QW + c) = v;
-      if (p.qg0) *reinterpret_cast<float2*>(p.qg0 + (base + m) * QW + c) = v;
-    });
+    tile_gemm_wide_mma(                                              // Q~g = A_g · g + a_c
+        Xs, p.w.ag_t, Wb, [&](int, int c) { return *reinterpret_cast<const float2*>(p.w.a_c + c); },
+        [&](int m, int c, float v0, float v1) {
+          if (m >= cnt) return;
+          const float2 v = make_float2(v0, v1);
+          *reinterpret_cast<float2*>(p.qg + (base + m) * QW + c) = v;
+          if (p.qg0) *reinterpret_cast<float2*>(p.qg0 + (base + m) * QW + c) = v;
+        });
     __syncthreads();
   }
 
@@ -120,25 +121,28 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         }
       } else {
         if (t == 1 && kind != VRPX_IRP) {
-          tile_gemm_wide_mma(Xs, p.w.af_t, Wb, [&](int m, int c, float v0, float v1) {   // fold `first` (graph_decoder.py:111-113)
-            if (m >= cnt) return;
-            float2* qgp = reinterpret_cast<float2*>(p.qg + (base + m) * QW + c);
-            const float2 q = *qgp;
-            *qgp = make_float2(q.x + v0, q.y + v1);
-          });
-          __syncthreads();  // qg updates are re-read by other threads' epilogue below? (same thread) — keep ordering explicit
+          tile_gemm_wide_mma(                                        // fold `first` (graph_decoder.py:111-113)
+              Xs, p.w.af_t, Wb,
+              [&](int m, int c) {
+                return (m < cnt) ? *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c) : make_float2(0.f, 0.f);
+              },
+              [&](int m, int c, float v0, float v1) {
+                if (m < cnt) *reinterpret_cast<float2*>(p.qg + (base + m) * QW + c) = make_float2(v0, v1);
+              });
         }
-        tile_gemm_wide_mma(Xs, p.w.al_t, Wb, [&](int m, int c, float v0, float v1) {   // q~ = A_l · h[last] + Q~g (+ load · a_load)
-          if (m >= cnt) return;
-          const float2 q = *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c);
-          float2 v = make_float2(v0 + q.x, v1 + q.y);
-          if (kind == VRPX_IRP) {
-            const float2 al = *reinterpret_cast<const float2*>(p.w.a_load + c);
-            const float lf = s_loadf[m];
-            v = make_float2(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y));
-          }
-          *reinterpret_cast<float2*>(QC + m * QC_LD + c) = v;
-        });
+        tile_gemm_wide_mma(                                          // q~ = Q~g (+ load · a_load) + A_l · h[last]
+            Xs, p.w.al_t, Wb,
+            [&](int m, int c) {
+              if (m >= cnt) return make_float2(0.f, 0.f);
+              float2 q = *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c);
+              if (kind == VRPX_IRP) {
+                const float2 al = *reinterpret_cast<const float2*>(p.w.a_load + c);
+                const float lf = s_loadf[m];
+                q = make_float2(fmaf(lf, al.x, q.x), fmaf(lf, al.y, q.y));
+              }
+              return q;
+            },
+            [&](int m, int c, float v0, float v1) { *reinterpret_cast<float2*>(QC + m * QC_LD + c) = make_float2(v0, v1); });
       }
       __syncthreads();
 

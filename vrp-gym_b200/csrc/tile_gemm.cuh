@@ -216,13 +216,11 @@ __device__ __forceinline__ void tile_gemm_tall(float* __restrict__ Cs, const flo
 // Shared-memory leading dimensions are padded so that fragment loads are bank-conflict free:
 constexpr int XS_LD = E + 4;        // 132: A fragments (row g, col t): bank (4g + t) % 32
 constexpr int QC_LD = QW + 4;       // 1028
-constexpr int WIDE_LD = QW + 8;     // 1032: B fragments (k = t, n = g): bank (8t + g) % 32
-constexpr int TALL_LD = E + 8;      // 136
-constexpr int WIDE_CHUNK_FLOATS = 8 * WIDE_LD;    // one mma k-step (8 k-rows) of all 1024 columns, 33 KiB
-constexpr int TALL_CHUNK_FLOATS = 64 * TALL_LD;   // 8 k-groups x 8 k-rows x 128 columns, 34.8 KiB
+constexpr int WARP_LD = 64 + 8;     // 72: per-warp weight stage [8 k-rows][64 columns], B fragments (k = t, n = g): bank (8t + g) % 32
+constexpr int WARP_STAGE_FLOATS = 8 * WARP_LD;            // 576 floats = 2304 B: one mma k-step of a warp's 64 columns
 constexpr size_t SMEM_X_MMA = (size_t)TM * XS_LD * sizeof(float);
 constexpr size_t SMEM_QC_MMA = (size_t)TM * QC_LD * sizeof(float);
-constexpr size_t SMEM_W_MMA = 2 * (size_t)TALL_CHUNK_FLOATS * sizeof(float);
+constexpr size_t SMEM_W_MMA = (size_t)(NT / 32) * 2 * WARP_STAGE_FLOATS * sizeof(float);   // 16 warps x 2 stages = 72 KiB
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(x) & 0xffffe000u;
@@ -248,48 +246,42 @@ __device__ __forceinline__ void load_a_frags(const float* __restrict__ A, int ld
   }
 }
 
-__device__ __forceinline__ void stage_wide_chunk_mma(const float* __restrict__ Wt, int kstep, float* __restrict__ dst) {
-  const float* src = Wt + (size_t)kstep * 8 * QW;
+// Each warp streams ITS OWN 64 weight columns (8 k-rows = one mma k-step per stage, double buffered with cp.async), so
+// the k loop needs no CTA-wide barrier — only __syncwarp.  src points at element (k = 0, first column of the warp).
+__device__ __forceinline__ void stage_warp_kstep(const float* __restrict__ src, int ld, int kstep, float* __restrict__ dst,
+                                                 int lane) {
 #pragma unroll
-  for (int i = 0; i < 2048 / NT; ++i) {
-    int idx = threadIdx.x + NT * i;       // 8 rows x 256 float4
-    int r = idx >> 8, c4 = idx & 255;
-    cp_async16(dst + r * WIDE_LD + c4 * 4, src + (size_t)r * QW + c4 * 4);
+  for (int i = 0; i < 4; ++i) {
+    const int idx = lane + 32 * i;        // 8 rows x 16 float4
+    const int r = idx >> 4, c4 = idx & 15;
+    cp_async16(dst + r * WARP_LD + c4 * 4, src + (size_t)(kstep * 8 + r) * ld + c4 * 4);
   }
 }
 
-// out[32][1024] = Xs[32][128] (ld XS_LD) · Wt[128][1024].  Warp w owns columns [64w, 64w + 64).
-// epi(m, c, v0, v1): row m, columns c and c+1.
-template <class Epi>
-__device__ __forceinline__ void tile_gemm_wide_mma(const float* __restrict__ Xs, const float* __restrict__ Wt,
-                                                   float* __restrict__ Wb, Epi epi) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  float acc[2][8][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
-  stage_wide_chunk_mma(Wt, 0, Wb);
+// acc[2][8][4] += A[32][K = 8*nks] (smem, leading dim lda, k offset k_base) · W[k][64 columns of this warp]
+__device__ __forceinline__ void warp_gemm_mma(float (&acc)[2][8][4], const float* __restrict__ A, int lda, int k_base,
+                                              const float* __restrict__ wsrc, int wld, int nks, float* __restrict__ wbuf,
+                                              int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  stage_warp_kstep(wsrc, wld, 0, wbuf, lane);
   cp_async_commit();
-  for (int ks = 0; ks < 16; ++ks) {
-    if (ks + 1 < 16) {
-      stage_wide_chunk_mma(Wt, ks + 1, Wb + ((ks + 1) & 1) * TALL_CHUNK_FLOATS);
+  for (int ks = 0; ks < nks; ++ks) {
+    if (ks + 1 < nks) {
+      stage_warp_kstep(wsrc, wld, ks + 1, wbuf + ((ks + 1) & 1) * WARP_STAGE_FLOATS, lane);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
+    __syncwarp();
     uint32_t ah[2][4], al[2][4];
-    load_a_frags(Xs, XS_LD, ks * 8, g, t, ah, al);
-    const float* wb = Wb + (ks & 1) * TALL_CHUNK_FLOATS + warp * 64 + g;
+    load_a_frags(A, lda, k_base + ks * 8, g, t, ah, al);
+    const float* wb = wbuf + (ks & 1) * WARP_STAGE_FLOATS + g;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint32_t bh0, bl0, bh1, bl1;
-      split_tf32(wb[t * WIDE_LD + 8 * j], bh0, bl0);
-      split_tf32(wb[(t + 4) * WIDE_LD + 8 * j], bh1, bl1);
+      split_tf32(wb[t * WARP_LD + 8 * j], bh0, bl0);
+      split_tf32(wb[(t + 4) * WARP_LD + 8 * j], bh1, bl1);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         mma_tf32_16x8x8(acc[mt][j], al[mt], bh0, bh1);
@@ -297,8 +289,27 @@ __device__ __forceinline__ void tile_gemm_wide_mma(const float* __restrict__ Xs,
         mma_tf32_16x8x8(acc[mt][j], ah[mt], bh0, bh1);
       }
     }
-    __syncthreads();
+    __syncwarp();  // all lanes are done with this stage before the next iteration refills it
   }
+}
+
+// out[32][1024] = init + Xs[32][128] (ld XS_LD) · Wt[128][1024].  Warp w owns columns [64w, 64w + 64).
+// init(m, c) -> float2 start value for (row m, columns c, c+1), fetched BEFORE the k loop so that its global-memory
+// latency hides behind the weight pipeline; epi(m, c, v0, v1) stores the result.
+template <class Init, class Epi>
+__device__ __forceinline__ void tile_gemm_wide_mma(const float* __restrict__ Xs, const float* __restrict__ Wt,
+                                                   float* __restrict__ Wb, Init init, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = warp * 64 + 8 * j + 2 * t;
+      const float2 i0 = init(mt * 16 + g, c), i1 = init(mt * 16 + g + 8, c);
+      acc[mt][j][0] = i0.x; acc[mt][j][1] = i0.y; acc[mt][j][2] = i1.x; acc[mt][j][3] = i1.y;
+    }
+  warp_gemm_mma(acc, Xs, XS_LD, 0, Wt + warp * 64, QW, 16, Wb + warp * 2 * WARP_STAGE_FLOATS, lane);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -309,19 +320,9 @@ __device__ __forceinline__ void tile_gemm_wide_mma(const float* __restrict__ Xs,
     }
 }
 
-__device__ __forceinline__ void stage_tall_chunk_mma(const float* __restrict__ Mt, int kc, float* __restrict__ dst) {
-#pragma unroll
-  for (int i = 0; i < 2048 / NT; ++i) {
-    int idx = threadIdx.x + NT * i;       // 64 rows x 32 float4
-    int row = idx >> 5, c4 = idx & 31;    // row = kg * 8 + r
-    int k = (row >> 3) * 128 + kc * 8 + (row & 7);
-    cp_async16(dst + row * TALL_LD + c4 * 4, Mt + (size_t)k * E + c4 * 4);
-  }
-}
-
 // out[32][128] (ld out_ld) = Cs[32][1024] (ld QC_LD) · Mt[1024][128] + bias.  Warp (kg = w >> 1, ng = w & 1) owns
 // columns [64 ng, 64 ng + 64) over the k range [128 kg, 128 kg + 128); the 8 partial sums go through `part`
-// ([8][32][128] floats, may alias Cs).
+// ([8][32][128] floats, may alias Cs).  The caller must have synchronised the CTA after writing Cs.
 __device__ __forceinline__ void tile_gemm_tall_mma(float* __restrict__ Cs, const float* __restrict__ Mt,
                                                    float* __restrict__ Wb, const float* __restrict__ bias,
                                                    float* __restrict__ part, float* __restrict__ out, int out_ld) {
@@ -334,34 +335,9 @@ __device__ __forceinline__ void tile_gemm_tall_mma(float* __restrict__ Cs, const
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
-  stage_tall_chunk_mma(Mt, 0, Wb);
-  cp_async_commit();
-  for (int kc = 0; kc < 16; ++kc) {
-    if (kc + 1 < 16) {
-      stage_tall_chunk_mma(Mt, kc + 1, Wb + ((kc + 1) & 1) * TALL_CHUNK_FLOATS);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    uint32_t ah[2][4], al[2][4];
-    load_a_frags(Cs, QC_LD, kg * 128 + kc * 8, g, t, ah, al);
-    const float* wb = Wb + (kc & 1) * TALL_CHUNK_FLOATS + kg * 8 * TALL_LD + ng * 64 + g;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t bh0, bl0, bh1, bl1;
-      split_tf32(wb[t * TALL_LD + 8 * j], bh0, bl0);
-      split_tf32(wb[(t + 4) * TALL_LD + 8 * j], bh1, bl1);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        mma_tf32_16x8x8(acc[mt][j], al[mt], bh0, bh1);
-        mma_tf32_16x8x8(acc[mt][j], ah[mt], bl0, bl1);
-        mma_tf32_16x8x8(acc[mt][j], ah[mt], bh0, bh1);
-      }
-    }
-    __syncthreads();  // also orders the last reads of Cs before `part` (which may alias it) is written
-  }
+  warp_gemm_mma(acc, Cs, QC_LD, kg * 128, Mt + (size_t)kg * 128 * E + ng * 64, E, 16, Wb + warp * 2 * WARP_STAGE_FLOATS,
+                lane);
+  __syncthreads();  // every warp is done reading Cs before `part` (which may alias it) is written
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
