@@ -39,9 +39,17 @@ struct RolloutParams {
   float* load_hist;   // optional [Tmax][B] f32 vehicle load before each step (backward)
   unsigned* bar;      // grid barrier counter
   int* notdone;       // [Tmax + 1]
+  long long* prof;    // optional [8] cycle counters per phase (debug, vrpx_debug_rollout_profile)
 };
 
 constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_MMA;   // 16.5 + 128.5 + 72 KiB
+
+// Pull one instance's embeddings (N rows of 512 B) towards L2 ahead of their first use in a step: the first pass over
+// h would otherwise pay HBM latency on every row tile.
+__device__ __forceinline__ void prefetch_instance_l2(const float* hb, int N, int lane) {
+  const char* base = reinterpret_cast<const char*>(hb);
+  for (int i = lane; i < N * 4; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
+}
 
 // ---------------------------------------------------------------- the persistent kernel
 __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
@@ -49,8 +57,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
   float* Xs = reinterpret_cast<float*>(smem_raw);
   float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA);
   float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA + SMEM_QC_MMA);
-  __shared__ float s_loadf[TM];
-  __shared__ int s_anyleft;
+  __shared__ float s_loadf[TM], s_lp[TM];
+  __shared__ int s_anyleft, s_act[TM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.env.N, kind = p.env.kind;
@@ -58,6 +66,13 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
   const int64_t ntiles = (B + TM - 1) / TM;
   const float* __restrict__ h = p.h;
   unsigned bar_target = 0;
+  long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VRPX_PROF(i)                                   \
+  if (p.prof && tid == 0) {                            \
+    long long now_ = clock64();                        \
+    prof_acc[i] += now_ - prof_t;                      \
+    prof_t = now_;                                     \
+  }
 
   // ------------------------------------------------ prologue: Q~g[b] = A_g · mean_n h[b,n] + a_c
   for (int64_t tile = blockIdx.x; tile < ntiles && p.t0 == 0; tile += gridDim.x) {
@@ -96,7 +111,9 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       const int64_t base = tile * TM;
       const int cnt = (int)((B - base < TM) ? (B - base) : TM);
       if (tid == 0) s_anyleft = 0;
-      // ---------------- P0: gather last-node embeddings, vehicle load
+      // ---------------- P0: gather last-node embeddings, vehicle load; pull this tile's Q~g rows towards L2
+      for (int i = tid; i < cnt * 32; i += NT)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.qg + base * QW) + (size_t)i * 128));
       for (int m = warp; m < TM; m += NT / 32) {
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < cnt && t > 0) {
@@ -111,6 +128,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         if (m < cnt && p.load_hist && lane == 0) p.load_hist[(int64_t)trel * B + base + m] = lf;
       }
       __syncthreads();
+      VRPX_PROF(0)
       // ---------------- P1: q~
       if (t == 0) {
         for (int o = tid; o < cnt * QW; o += NT) {
@@ -145,6 +163,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
             [&](int m, int c, float v0, float v1) { *reinterpret_cast<float2*>(QC + m * QC_LD + c) = make_float2(v0, v1); });
       }
       __syncthreads();
+      VRPX_PROF(1)
 
       // ---------------- P2: glimpse attention, one warp per instance
       for (int m = warp; m < cnt; m += NT / 32) {
@@ -170,7 +189,15 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
         for (int n0 = 0; n0 < N; n0 += 16) {
           const int na = n0 + g, nbb = n0 + g + 8;
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          // six independent accumulator chains (3 split terms x even/odd k-step): a single chain would serialise the
+          // 96 mma of a node tile on the tensor-pipe latency
+          float acc6[2][3][4];
+#pragma unroll
+          for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+            for (int b_ = 0; b_ < 3; ++b_)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc6[a_][b_][i] = 0.f;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float4 va[4], vb[4];
@@ -195,12 +222,16 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
                 split_tf32(be[2 * u + 1], ah[3], al[3]);   // (row g+8, k = t+4)
                 split_tf32(qe[2 * u], bh0, bl0);           // (k = t,   n = g)
                 split_tf32(qe[2 * u + 1], bh1, bl1);       // (k = t+4, n = g)
-                mma_tf32_16x8x8(acc, al, bh0, bh1);
-                mma_tf32_16x8x8(acc, ah, bl0, bl1);
-                mma_tf32_16x8x8(acc, ah, bh0, bh1);
+                mma_tf32_16x8x8(acc6[u][0], al, bh0, bh1);
+                mma_tf32_16x8x8(acc6[u][1], ah, bl0, bl1);
+                mma_tf32_16x8x8(acc6[u][2], ah, bh0, bh1);
               }
             }
           }
+          float acc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            acc[i] = ((acc6[0][0][i] + acc6[1][0][i]) + (acc6[0][1][i] + acc6[1][1][i])) + (acc6[0][2][i] + acc6[1][2][i]);
           // C fragment: acc[0], acc[1] = node na, heads 2t, 2t+1;  acc[2], acc[3] = node nbb
           if (na < N) {
             slot[(2 * t) * E + na] = acc[0] + (float)((nb0[na >> 5] >> (na & 31)) & 1u);
@@ -212,6 +243,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           }
         }
         __syncwarp();
+        VRPX_PROF(6)
         // softmax per head over nodes (lane = node, 4 strides cover N <= 128)
         float pr[NH][4];
 #pragma unroll
@@ -247,6 +279,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           }
         }
         __syncwarp();
+        VRPX_PROF(7)
         // ---- pass 2 on the tensor pipe: c[head][dim] = sum_n P[n][head] h_n[dim]  (M = 16 dims, N = 8 heads, K = 8 nodes)
         // Thread g streams the float4 chunks 8c' + g (dims 32c' + 4g + e) of node rows n0+t and n0+t+4; m-tile
         // j = 2c' + u has row g <-> dim 32c'+4g+2u and row g+8 <-> dim 32c'+4g+2u+1.  B = P[n][head] from the slot.
@@ -298,10 +331,12 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       // rows >= cnt of C must be finite for GEMM-B (results unused): zero them
       for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[(o >> 10) * QC_LD + (o & (QW - 1))] = 0.f;
       __syncthreads();
+      VRPX_PROF(2)
 
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
       tile_gemm_tall_mma(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
 
+      VRPX_PROF(3)
       // ---------------- P4: logits, action, environment transition
       bool unfinished = false;
       for (int m = warp; m < cnt; m += NT / 32) {
@@ -400,45 +435,57 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           float ua = __shfl_sync(0xffffffffu, usel, a >> 2);
           lp = (ua - mx) - logf(total);
         }
-        if (lane == 0) {
-          if (p.tape && p.mode != VRPX_TEACHER) p.tape[(int64_t)trel * B + b] = (uint8_t)a;
-          Bits128 v;
+        if (lane == 0) { s_act[m] = a; s_lp[m] = lp; }
+      }
+      __syncthreads();
+      // environment transition: one THREAD per instance, so the dependent global loads (state -> coordinates) of the
+      // whole tile overlap instead of running back to back on lane 0 of each warp
+      if (tid < cnt) {
+        const int m = tid;
+        const int64_t b = base + m;
+        const int a = s_act[m];
+        if (p.tape && p.mode != VRPX_TEACHER) p.tape[(int64_t)trel * B + b] = (uint8_t)a;
+        Bits128 v;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v.w[i] = p.env.visited[b * 4 + i];
-          int cur = p.env.cur[b];
-          double load = p.env.load[b];
-          const int depot = p.env.depot[b];
-          const double* dem = p.env.demand ? p.env.demand + b * N : nullptr;
-          StepResult r = env_transition(kind, N, p.env.xy + b * N * 2, dem, depot, a, v, cur, load);
-          p.env.cur[b] = cur;
-          p.env.load[b] = load;
+        for (int i = 0; i < 4; ++i) v.w[i] = p.env.visited[b * 4 + i];
+        int cur = p.env.cur[b];
+        double load = p.env.load[b];
+        const int depot = p.env.depot[b];
+        const double* dem = p.env.demand ? p.env.demand + b * N : nullptr;
+        StepResult r = env_transition(kind, N, p.env.xy + b * N * 2, dem, depot, a, v, cur, load);
+        p.env.cur[b] = cur;
+        p.env.load[b] = load;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) p.env.visited[b * 4 + i] = v.w[i];
-          if (kind == VRPX_IRP) {
-            Bits128 x = demand_exceeds(dem, N, load);
+        for (int i = 0; i < 4; ++i) p.env.visited[b * 4 + i] = v.w[i];
+        if (kind == VRPX_IRP) {
+          Bits128 x = demand_exceeds(dem, N, load);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) p.env.mask[b * 4 + i] = v.w[i] | x.w[i];
-          }
-          // f32 accumulation of f32(reward) in step order (graph_tsp_agent.py:85); cost = -acc_loss
-          p.cost[b] = (t == 0 ? 0.f : p.cost[b]) + (float)r.dist;
-          if (p.mode != VRPX_GREEDY) p.logp[b] = (t == 0 ? 0.f : p.logp[b]) + lp;
-          else if (t == 0) p.logp[b] = 0.f;
-          if (!r.all_before) unfinished = true;
+          for (int i = 0; i < 4; ++i) p.env.mask[b * 4 + i] = v.w[i] | x.w[i];
         }
+        // f32 accumulation of f32(reward) in step order (graph_tsp_agent.py:85); cost = -acc_loss
+        p.cost[b] = (t == 0 ? 0.f : p.cost[b]) + (float)r.dist;
+        if (p.mode != VRPX_GREEDY) p.logp[b] = (t == 0 ? 0.f : p.logp[b]) + s_lp[m];
+        else if (t == 0) p.logp[b] = 0.f;
+        if (!r.all_before) unfinished = true;
       }
       if (unfinished) s_anyleft = 1;  // benign race: all writers store 1
       __syncthreads();
       if (s_anyleft) cta_unfinished = true;
       __syncthreads();
+      VRPX_PROF(4)
     }
     if (tid == 0 && cta_unfinished) atomicAdd(p.notdone + trel, 1);
     bar_target += gridDim.x;
     grid_barrier(p.bar, bar_target);
+    VRPX_PROF(5)
     if (ld_acquire_i(p.notdone + trel) == 0) { ++t; break; }
   }
+  if (p.prof && tid == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(p.prof) + i, (unsigned long long)prof_acc[i]);
   if (blockIdx.x == 0 && tid == 0) *p.steps = t;
 }
 
+static long long* g_rollout_prof = nullptr;
 constexpr int64_t kRolloutSmall = 4096;  // barrier counter + notdone[<=513]
 
 }  // namespace vrpx
@@ -446,6 +493,9 @@ constexpr int64_t kRolloutSmall = 4096;  // barrier counter + notdone[<=513]
 using namespace vrpx;
 
 extern "C" {
+
+/* Debug hook: device buffer of 8 x int64 that accumulates per-phase cycles of thread 0 of every CTA (NULL disables). */
+VRPX_API void vrpx_debug_rollout_profile(long long* dev_counters) { g_rollout_prof = dev_counters; }
 
 int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N) {
   (void)N;
@@ -488,6 +538,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   p.qg0 = trace ? trace->qg0 : nullptr;
   p.mask_hist = trace ? trace->mask_hist : nullptr;
   p.load_hist = trace ? trace->load_hist : nullptr;
+  p.prof = g_rollout_prof;
   p.bar = reinterpret_cast<unsigned*>(ws);
   p.notdone = reinterpret_cast<int*>(ws) + 8;
   p.qg = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kRolloutSmall);
