@@ -37,7 +37,7 @@ SHAPES = [(128, 128, 128), (1000, 128, 384), (777, 128, 512), (1300, 512, 128), 
           (70000, 128, 384)]
 
 
-@pytest.mark.parametrize("path", [1, 2, 0], ids=["simt", "tcgen05_v1", "tcgen05"])
+@pytest.mark.parametrize("path", [1, 2, 3, 0], ids=["simt", "tcgen05_v1", "tcgen05_v2", "tcgen05"])
 @pytest.mark.parametrize("R,K,NOUT", SHAPES)
 def test_gemm_plain(path, R, K, NOUT):
     Y, ref = _run(path, R, K, NOUT, False, False, False, False)
@@ -50,7 +50,7 @@ def test_gemm_plain(path, R, K, NOUT):
     assert err <= tol, (path, R, K, NOUT, err, scale)
 
 
-@pytest.mark.parametrize("path", [1, 2, 0], ids=["simt", "tcgen05_v1", "tcgen05"])
+@pytest.mark.parametrize("path", [1, 2, 3, 0], ids=["simt", "tcgen05_v1", "tcgen05_v2", "tcgen05"])
 def test_gemm_epilogues(path):
     for (bias, relu, residual, bn) in [(True, False, False, False), (True, True, False, False),
                                        (True, False, True, True), (False, False, True, False)]:

@@ -23,11 +23,12 @@ struct GemmArgs {
 };
 
 int gemm_simt(const GemmArgs& a, cudaStream_t stream);  // fp32 FFMA, smem tiled
-int gemm_tc(const GemmArgs& a, cudaStream_t stream);    // tcgen05.mma kind::tf32, 3-term split (≈fp32); persistent, TMA-staged (gemm_tc2.cu)
+int gemm_tc(const GemmArgs& a, cudaStream_t stream);    // tcgen05.mma kind::tf32, 3-term split (≈fp32); persistent, TMA-staged, A operand in TMEM (gemm_tc3.cu)
 int gemm_tc_v1(const GemmArgs& a, cudaStream_t stream); // first-generation tcgen05 kernel (gemm_tc.cu), cross-check
+int gemm_tc_v2(const GemmArgs& a, cudaStream_t stream); // persistent TMA kernel with both operands in smem (gemm_tc2.cu)
 
 inline int gemm_dispatch(int path, const GemmArgs& a, cudaStream_t stream) {
-  return path == 0 ? gemm_tc(a, stream) : (path == 2 ? gemm_tc_v1(a, stream) : gemm_simt(a, stream));
+  return path == 0 ? gemm_tc(a, stream) : (path == 2 ? gemm_tc_v1(a, stream) : (path == 3 ? gemm_tc_v2(a, stream) : gemm_simt(a, stream)));
 }
 
 }  // namespace vrpx

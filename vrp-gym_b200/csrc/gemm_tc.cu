@@ -225,5 +225,6 @@ extern "C" int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float
   vrpx::GemmArgs g{X, R, K, W, NOUT, bias, relu, residual, scale, shift, Y};
   if (path == 0) return vrpx::gemm_tc(g, (cudaStream_t)stream);
   if (path == 2) return vrpx::gemm_tc_v1(g, (cudaStream_t)stream);
+  if (path == 3) return vrpx::gemm_tc_v2(g, (cudaStream_t)stream);
   return vrpx::gemm_simt(g, (cudaStream_t)stream);
 }

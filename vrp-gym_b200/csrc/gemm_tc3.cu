@@ -1,4 +1,11 @@
-// gemm_tc2.cu — persistent, warp-specialised tcgen05 GEMM (3xTF32) with TMA-staged operand tiles.
+// gemm_tc3.cu — persistent, warp-specialised tcgen05 GEMM (3xTF32): TMA-staged tiles, A operand fed from TMEM.
+//
+// Same pipeline as gemm_tc2.cu, with one change that removes the shared-memory bandwidth ceiling measured there
+// (l1tex 60-75 % busy, tensor pipe 12-30 %): a 128x128xK=8 tf32 MMA reads 4 KiB of A and 4 KiB of B from smem every
+// 64 cycles, which by itself saturates the 128 B/clk shared-memory port once the converters' traffic is added.  Here
+// the converter warps write the hi / lo halves of the X tile straight into TENSOR MEMORY (tcgen05.st, lane = tile row,
+// one 32-bit column per k element) and the MMAs take A from TMEM, so shared memory only carries the raw TMA tiles
+// and the B (weight) operand.
 //
 //   Y[R][NOUT] = epilogue( X[R][K] · W[NOUT][K]^T ),  fp32 in / fp32 out, ~fp32 accuracy (see gemm_tc.cu for the
 //   precision policy: D = Xlo·Whi + Xhi·Wlo + Xhi·Whi on tcgen05.mma kind::tf32, fp32 accumulators in TMEM).
@@ -15,13 +22,15 @@
 #include "gemm.cuh"
 
 namespace vrpx {
-namespace tc2 {
+namespace tc3 {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int NTHREADS = 384;
 constexpr int TILE_BYTES = BM * BK * 4;        // 16 KiB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // X raw/hi | X lo | W raw/hi | W lo
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;    // X raw | W raw/hi | W lo   (X hi/lo live in TMEM)
+constexpr uint32_t TMEM_A0 = 2 * BN;            // TMEM columns: 2 accumulators, then STAGES x (32 hi + 32 lo) A columns
+constexpr uint32_t TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -70,6 +79,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -91,8 +108,39 @@ __device__ __forceinline__ void split_tile(unsigned char* raw_hi, unsigned char*
   }
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+// Row r (= converter thread) of the raw X tile: 8 swizzled 16-byte chunks -> 32 hi + 32 lo words in TMEM lane r.
+__device__ __forceinline__ void x_tile_to_tmem(const unsigned char* raw, int r, uint32_t taddr_hi) {
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(raw + r * 128 + ((c ^ (r & 7)) << 4));
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t h = __float_as_uint(e[i]) & 0xffffe000u;
+      hi[4 * c + i] = h;
+      lo[4 * c + i] = __float_as_uint(e[i] - __uint_as_float(h));
+    }
+  }
+  tmem_st32(taddr_hi, hi);
+  tmem_st32(taddr_hi + 32, lo);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_gemm_tc2(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW) {
+k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t s_raw_full[STAGES], s_conv_done[STAGES], s_stage_free[STAGES], s_acc_full[2], s_acc_free[2];
   __shared__ uint32_t s_tmem;
@@ -117,7 +165,7 @@ k_gemm_tc2(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -138,7 +186,7 @@ k_gemm_tc2(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
           const uint32_t bar = smem_u32(&s_raw_full[s]);
           mbar_expect_tx(bar, 2 * TILE_BYTES);
           tma_load_2d(smem_u32(st), &mapX, kb * BK, row0, bar);
-          tma_load_2d(smem_u32(st + 2 * TILE_BYTES), &mapW, kb * BK, col0, bar);
+          tma_load_2d(smem_u32(st + TILE_BYTES), &mapW, kb * BK, col0, bar);
         }
       }
     }
@@ -150,9 +198,10 @@ k_gemm_tc2(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
         const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
         unsigned char* st = smem + s * STAGE_BYTES;
         mbar_wait(smem_u32(&s_raw_full[s]), ph);
-        split_tile(st, st + TILE_BYTES, tid);
-        split_tile(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+        x_tile_to_tmem(st, tid, tmem + ((uint32_t)(warp * 32) << 16) + TMEM_A0 + s * 64);
+        split_tile(st + TILE_BYTES, st + 2 * TILE_BYTES, tid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_conv_done[s]));
       }
@@ -171,14 +220,14 @@ k_gemm_tc2(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
           unsigned char* st = smem + s * STAGE_BYTES;
           mbar_wait(smem_u32(&s_conv_done[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t xh = make_desc(smem_u32(st)), xl = make_desc(smem_u32(st + TILE_BYTES));
-          const uint64_t wh = make_desc(smem_u32(st + 2 * TILE_BYTES)), wl = make_desc(smem_u32(st + 3 * TILE_BYTES));
+          const uint32_t ah = tmem + TMEM_A0 + s * 64, alo = ah + 32;
+          const uint64_t wh = make_desc(smem_u32(st + TILE_BYTES)), wl = make_desc(smem_u32(st + 2 * TILE_BYTES));
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint64_t o = (uint64_t)(2 * j);
-            mma_tf32(d, xl + o, wh + o, (kb | j) ? 1u : 0u);
-            mma_tf32(d, xh + o, wl + o, 1u);
-            mma_tf32(d, xh + o, wh + o, 1u);
+            mma_tf32_ts(d, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u);
+            mma_tf32_ts(d, ah + 8 * j, wl + o, 1u);
+            mma_tf32_ts(d, ah + 8 * j, wh + o, 1u);
           }
           mma_commit(smem_u32(&s_stage_free[s]));
         }
@@ -244,7 +293,7 @@ k_gemm_tc2(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -285,10 +334,10 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int cols) {
   return VRPX_OK;
 }
 
-}  // namespace tc2
+}  // namespace tc3
 
-int gemm_tc_v2(const GemmArgs& a, cudaStream_t stream) {
-  using namespace tc2;
+int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
+  using namespace tc3;
   if (a.K % BK != 0 || a.NOUT % BN != 0 || a.R <= 0) {
     set_error("gemm_tc: unsupported shape R=%lld K=%d NOUT=%d", (long long)a.R, a.K, a.NOUT);
     return VRPX_ERR_ARG;
@@ -303,12 +352,12 @@ int gemm_tc_v2(const GemmArgs& a, cudaStream_t stream) {
   if ((rc = make_map(&mw, a.W, a.NOUT, a.K))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   const int64_t ntiles = ((a.R + BM - 1) / BM) * (a.NOUT / BN);
   const int grid = (int)((ntiles < (int64_t)num_sms()) ? ntiles : (int64_t)num_sms());
-  k_gemm_tc2<<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mw);
+  k_gemm_tc3<<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mw);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }
