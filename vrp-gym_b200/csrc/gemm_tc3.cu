@@ -31,7 +31,7 @@ constexpr int TILE_BYTES = BM * BK * 4;        // 16 KiB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;    // X raw | W raw/hi | W lo   (X hi/lo live in TMEM)
 constexpr uint32_t TMEM_A0 = 2 * BN;            // TMEM columns: 2 accumulators, then STAGES x (32 hi + 32 lo) A columns
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4096 + 1024;   // stages | 4 epilogue transpose patches | alignment slack
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -236,11 +236,17 @@ k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     }
   } else if (warp >= 8) {
     // ===================== epilogue =====================
+    // tcgen05.ld hands every thread one tile ROW (32 consecutive columns).  Storing that directly would touch 32
+    // different 128-byte lines per instruction, so each 32x32 chunk is transposed through a 4 KiB swizzled smem patch:
+    // afterwards lane l owns columns 4(l&7)..+3 of rows 4i + (l>>3), i = 0..7, and every global load / store
+    // instruction of the warp covers 4 rows x 128 contiguous bytes.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    unsigned char* patch = smem + STAGES * STAGE_BYTES + q * 4096;
+    const int lr = lane >> 3, lc = lane & 7;
     uint32_t ti = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-      const int64_t r = (tile / nct) * BM + q * 32 + lane;
+      const int64_t row_base = (tile / nct) * BM + q * 32;
       const int col0 = (int)(tile % nct) * BN;
       mbar_wait(smem_u32(&s_acc_full[acc]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -258,31 +264,42 @@ k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr)
             : "memory");
+        const int c = col0 + cc * 32 + lc * 4;   // this lane's 4 columns after the transpose
+        // per-column epilogue constants and the (coalesced) residual / gate rows are fetched while the TMEM load is in flight
+        const float4 bias4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 sc4 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 sh4 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.shift + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 res[8], gt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = row_base + 4 * i + lr;
+          res[i] = (a.residual && r < a.R) ? *reinterpret_cast<const float4*>(a.residual + r * a.NOUT + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gt[i] = (a.gate && r < a.R) ? *reinterpret_cast<const float4*>(a.gate + r * a.NOUT + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (r < a.R) {
-          const int c0 = col0 + cc * 32;
-          float* yrow = a.Y + r * a.NOUT + c0;
-          const float* rrow = a.residual ? a.residual + r * a.NOUT + c0 : nullptr;
-          const float* grow = a.gate ? a.gate + r * a.NOUT + c0 : nullptr;
+        __syncwarp();  // the previous chunk's reads of the patch are complete
 #pragma unroll
-          for (int g4 = 0; g4 < 8; ++g4) {
-            float o[4];
-            const float4 res = rrow ? *reinterpret_cast<const float4*>(rrow + 4 * g4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 gt = grow ? *reinterpret_cast<const float4*>(grow + 4 * g4) : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float rr[4] = {res.x, res.y, res.z, res.w}, gg[4] = {gt.x, gt.y, gt.z, gt.w};
+        for (int g4 = 0; g4 < 8; ++g4)
+          *reinterpret_cast<uint4*>(patch + lane * 128 + ((g4 ^ (lane & 7)) << 4)) = make_uint4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+        __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c0 + 4 * g4 + e;
-              float y = __uint_as_float(v[4 * g4 + e]);
-              if (!(gg[e] > 0.f)) y = 0.f;
-              if (a.bias) y += __ldg(a.bias + c);
-              if (a.relu) y = fmaxf(y, 0.f);
-              y += rr[e];
-              if (a.scale) y = fmaf(y, __ldg(a.scale + c), __ldg(a.shift + c));
-              o[e] = y;
-            }
-            *reinterpret_cast<float4*>(yrow + 4 * g4) = make_float4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + lr;
+          const int64_t r = row_base + rr;
+          const float4 x = *reinterpret_cast<const float4*>(patch + rr * 128 + ((lc ^ (rr & 7)) << 4));
+          float y[4] = {x.x, x.y, x.z, x.w};
+          const float gg[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w}, rs[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+          const float bb[4] = {bias4.x, bias4.y, bias4.z, bias4.w}, ss[4] = {sc4.x, sc4.y, sc4.z, sc4.w},
+                      hh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!(gg[e] > 0.f)) y[e] = 0.f;
+            y[e] += bb[e];
+            if (a.relu) y[e] = fmaxf(y[e], 0.f);
+            y[e] += rs[e];
+            if (a.scale) y[e] = fmaf(y[e], ss[e], hh[e]);
           }
+          if (r < a.R) *reinterpret_cast<float4*>(a.Y + r * a.NOUT + c) = make_float4(y[0], y[1], y[2], y[3]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
