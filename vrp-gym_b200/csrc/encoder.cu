@@ -189,6 +189,156 @@ __global__ void __launch_bounds__(256) k_enc_attention(const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------- per-instance self-attention on the tensor pipe
+// Same contract as k_enc_attention, computed with warp-level mma.sync.m16n8k8 TF32 and the 3-term split (~fp32):
+//   S = (Q/4) K^T  (16 queries x 8 keys per mma, 2 k-steps over dh = 16), row softmax in registers,
+//   O = P V        (the score accumulators are reused directly as A fragments: key order inside a key tile is
+//                   permuted, k-index t <-> key 2t, k-index t+4 <-> key 2t+1, and V is read with the same order).
+// One CTA per instance, one warp per head.  NTILES = ceil(N / 8) key tiles (compile-time bound on the registers).
+__device__ __forceinline__ void split_tf32_e(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_e(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma3_e(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                       uint32_t bl0, uint32_t bh1, uint32_t bl1) {
+  mma_tf32_e(c, al, bh0, bh1);
+  mma_tf32_e(c, ah, bl0, bl1);
+  mma_tf32_e(c, ah, bh0, bh1);
+}
+
+constexpr int ATT_VLD = 20;  // padded V row stride (floats): B fragments (key 2t / 2t+1, dim g) hit 32 distinct banks
+
+template <int NTILES>
+__global__ void __launch_bounds__(256) k_enc_attention_mma(const float* __restrict__ qkv, float* __restrict__ att, int N) {
+  extern __shared__ __align__(16) float sm[];
+  const int NP = NTILES * 8;                       // keys padded to a multiple of 8
+  float* Ks = sm;                                  // [8 heads][NP][16]
+  float* Vs = sm + (size_t)NH * NP * 16;           // [8 heads][NP][ATT_VLD]
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* base = qkv + b * N * 384;
+  for (int i = tid; i < NP * 64; i += 256) {       // 64 float4 per row of k|v
+    const int n = i >> 6, c4 = (i & 63) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) v = *reinterpret_cast<const float4*>(base + (int64_t)n * 384 + 128 + c4);
+    const int c = c4 & 127, hh = c >> 4, d = c & 15;
+    if (c4 < 128) *reinterpret_cast<float4*>(Ks + ((size_t)hh * NP + n) * 16 + d) = v;
+    else *reinterpret_cast<float4*>(Vs + ((size_t)hh * NP + n) * ATT_VLD + d) = v;
+  }
+  __syncthreads();
+  const int hh = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float* Kh = Ks + (size_t)hh * NP * 16;
+  const float* Vh = Vs + (size_t)hh * NP * ATT_VLD;
+  for (int q0 = 0; q0 < N; q0 += 16) {
+    const int qa = q0 + g, qb = q0 + g + 8;
+    // A fragments of Q/4: thread t owns dims 4t..4t+3; k-step u: k-index t <-> dim 4t+2u, t+4 <-> dim 4t+2u+1
+    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+    if (qa < N) xa = *reinterpret_cast<const float4*>(base + (int64_t)qa * 384 + hh * 16 + 4 * t);
+    if (qb < N) xb = *reinterpret_cast<const float4*>(base + (int64_t)qb * 384 + hh * 16 + 4 * t);
+    const float ea[4] = {xa.x * 0.25f, xa.y * 0.25f, xa.z * 0.25f, xa.w * 0.25f};
+    const float eb[4] = {xb.x * 0.25f, xb.y * 0.25f, xb.z * 0.25f, xb.w * 0.25f};
+    uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      split_tf32_e(ea[2 * u], qh[u][0], ql[u][0]);
+      split_tf32_e(eb[2 * u], qh[u][1], ql[u][1]);
+      split_tf32_e(ea[2 * u + 1], qh[u][2], ql[u][2]);
+      split_tf32_e(eb[2 * u + 1], qh[u][3], ql[u][3]);
+    }
+    // ---- S = (Q/4) K^T
+    float sc[NTILES][4];
+#pragma unroll
+    for (int j = 0; j < NTILES; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      const float4 kv = *reinterpret_cast<const float4*>(Kh + (8 * j + g) * 16 + 4 * t);   // key 8j+g, dims 4t..4t+3
+      const float ke[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32_e(ke[2 * u], bh0, bl0);
+        split_tf32_e(ke[2 * u + 1], bh1, bl1);
+        mma3_e(sc[j], qh[u], ql[u], bh0, bl0, bh1, bl1);
+      }
+    }
+    // ---- row softmax: thread holds keys 8j + 2t, 8j + 2t + 1 of rows qa (sc[j][0..1]) and qb (sc[j][2..3])
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NTILES; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = 8 * j + 2 * t + e < N;
+        if (!ok) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
+        ma = fmaxf(ma, sc[j][e]);
+        mb = fmaxf(mb, sc[j][2 + e]);
+      }
+    }
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTILES; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[j][e] = expf(sc[j][e] - ma);          // exp(-inf) = 0 for padded keys
+        sc[j][2 + e] = expf(sc[j][2 + e] - mb);
+        sa += sc[j][e];
+        sb += sc[j][2 + e];
+      }
+    }
+    sa += __shfl_xor_sync(0xffffffffu, sa, 1); sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+    sb += __shfl_xor_sync(0xffffffffu, sb, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+    // ---- O = P V  (A = P from the score registers; k-index t <-> key 8j+2t, t+4 <-> key 8j+2t+1)
+    float o[2][4];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTILES; ++j) {
+      uint32_t ph[4], pl[4];
+      split_tf32_e(sc[j][0], ph[0], pl[0]);   // (row g,   k = t)
+      split_tf32_e(sc[j][2], ph[1], pl[1]);   // (row g+8, k = t)
+      split_tf32_e(sc[j][1], ph[2], pl[2]);   // (row g,   k = t+4)
+      split_tf32_e(sc[j][3], ph[3], pl[3]);   // (row g+8, k = t+4)
+      const float* v0 = Vh + (8 * j + 2 * t) * ATT_VLD + g;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32_e(v0[8 * d], bh0, bl0);               // (k = t,   n = dim 8d+g) = V[key 8j+2t][8d+g]
+        split_tf32_e(v0[ATT_VLD + 8 * d], bh1, bl1);     // (k = t+4, n = dim 8d+g) = V[key 8j+2t+1][8d+g]
+        mma3_e(o[d], ph, pl, bh0, bl0, bh1, bl1);
+      }
+    }
+    const float ia = 1.0f / sa, ib = 1.0f / sb;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      if (qa < N) *reinterpret_cast<float2*>(att + (b * N + qa) * E + hh * 16 + 8 * d + 2 * t) = make_float2(o[d][0] * ia, o[d][1] * ia);
+      if (qb < N) *reinterpret_cast<float2*>(att + (b * N + qb) * E + hh * 16 + 8 * d + 2 * t) = make_float2(o[d][2] * ib, o[d][3] * ib);
+    }
+  }
+}
+
+static int launch_attention(const float* qkv, float* att, int64_t Bc, int N, cudaStream_t stream) {
+  const int nt = (N + 7) / 8;
+  const int NP = (nt <= 7 ? 7 : (nt <= 13 ? 13 : 16)) * 8;
+  const int smem = NH * NP * (16 + ATT_VLD) * (int)sizeof(float);
+  if (nt <= 7) {
+    VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_mma<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_enc_attention_mma<7><<<(unsigned)Bc, 256, smem, stream>>>(qkv, att, N);
+  } else if (nt <= 13) {
+    VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_mma<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_enc_attention_mma<13><<<(unsigned)Bc, 256, smem, stream>>>(qkv, att, N);
+  } else {
+    VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_enc_attention_mma<16><<<(unsigned)Bc, 256, smem, stream>>>(qkv, att, N);
+  }
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
 // ---------------------------------------------------------------- BatchNorm (graph_encoder.py:141-154)
 struct BnSlots {           // per BatchNorm instance, in the small workspace
   double sum[E], sq[E];    // train: column sums of y and y^2
@@ -341,11 +491,15 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
         qkv = Lb; att = Lb + R * 384; y1 = Lb + R * 512; h1 = Lb + R * 640; hid = Lb + R * 768; y2 = Lb + R * 1280;
         hout = (l + 1 < VRPX_LAYERS) ? saved + (int64_t)(l + 1) * R * 128 : h + b0 * N * E;
       }
-      int rc;
+      int rc = 0;
       GemmArgs g1{hc, R, E, L.in_proj_w, 3 * E, L.in_proj_b, 0, nullptr, nullptr, nullptr, qkv};
       if ((rc = gemm(g1, stream))) return rc;
-      k_enc_attention<<<(unsigned)Bc, 256, attn_smem, stream>>>(qkv, att, N);
-      VRPX_LAUNCH_CHECK();
+      if (gemm_path == 1) {  // fp32 SIMT cross-check path
+        k_enc_attention<<<(unsigned)Bc, 256, attn_smem, stream>>>(qkv, att, N);
+        VRPX_LAUNCH_CHECK();
+      } else if ((rc = launch_attention(qkv, att, Bc, N, stream))) {
+        return rc;
+      }
       if (!train) {
         GemmArgs g2{att, R, E, L.out_proj_w, E, L.out_proj_b, 0, hc, s1->scale, s1->shift, hc};
         if ((rc = gemm(g2, stream))) return rc;
