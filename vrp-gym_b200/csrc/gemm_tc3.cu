@@ -15,7 +15,8 @@
 //   warp 4      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 32 floats x 128 rows) for X and W
 //   warps 0-3   converters: split the raw fp32 tiles in place into hi (tf32-exact) + a second lo tile
 //   warp 5      MMA issuer: 12 tcgen05.mma per 32-wide k-block, tcgen05.commit releases the smem stage
-//   warps 8-11  epilogue: tcgen05.ld from one of TWO TMEM accumulators while the other is being filled
+//   warps 8-15  epilogue (two warps per TMEM lane quarter, two 32-column chunks each): tcgen05.ld from one of TWO
+//               TMEM accumulators while the other is being filled
 // Hand-offs are mbarriers: raw_full (TMA tx bytes) -> conv_done -> stage_free (commit), acc_full / acc_free.
 #include <cuda.h>
 
@@ -26,12 +27,12 @@ namespace tc3 {
 
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 4;
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 512;
 constexpr int TILE_BYTES = BM * BK * 4;        // 16 KiB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;    // X raw | W raw/hi | W lo   (X hi/lo live in TMEM)
 constexpr uint32_t TMEM_A0 = 2 * BN;            // TMEM columns: 2 accumulators, then STAGES x (32 hi + 32 lo) A columns
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * 4096 + 1024;   // stages | 4 epilogue transpose patches | alignment slack
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 + 1024;   // stages | 8 epilogue transpose patches | alignment slack
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,7 +161,7 @@ k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s_acc_full[i]), 1);
-      mbar_init(smem_u32(&s_acc_free[i]), 4);
+      mbar_init(smem_u32(&s_acc_free[i]), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,7 +242,8 @@ k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     // afterwards lane l owns columns 4(l&7)..+3 of rows 4i + (l>>3), i = 0..7, and every global load / store
     // instruction of the warp covers 4 rows x 128 contiguous bytes.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
-    unsigned char* patch = smem + STAGES * STAGE_BYTES + q * 4096;
+    const int chalf = (warp - 8) >> 2;   // this warp's pair of 32-column chunks
+    unsigned char* patch = smem + STAGES * STAGE_BYTES + (warp - 8) * 4096;
     const int lr = lane >> 3, lc = lane & 7;
     uint32_t ti = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
@@ -251,7 +253,7 @@ k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
       mbar_wait(smem_u32(&s_acc_full[acc]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 2 * chalf; cc < 2 * chalf + 2; ++cc) {
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * BN + cc * 32;
         asm volatile(
@@ -265,16 +267,15 @@ k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
             : "r"(taddr)
             : "memory");
         const int c = col0 + cc * 32 + lc * 4;   // this lane's 4 columns after the transpose
-        // per-column epilogue constants and the (coalesced) residual / gate rows are fetched while the TMEM load is in flight
         const float4 bias4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 sc4 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
         const float4 sh4 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.shift + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 res[8], gt[8];
+        // the (coalesced) residual rows are fetched while the TMEM load is in flight
+        float4 res[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int64_t r = row_base + 4 * i + lr;
           res[i] = (a.residual && r < a.R) ? *reinterpret_cast<const float4*>(a.residual + r * a.NOUT + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          gt[i] = (a.gate && r < a.R) ? *reinterpret_cast<const float4*>(a.gate + r * a.NOUT + c) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         __syncwarp();  // the previous chunk's reads of the patch are complete
@@ -288,7 +289,8 @@ k_gemm_tc3(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
           const int64_t r = row_base + rr;
           const float4 x = *reinterpret_cast<const float4*>(patch + rr * 128 + ((lc ^ (rr & 7)) << 4));
           float y[4] = {x.x, x.y, x.z, x.w};
-          const float gg[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w}, rs[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+          const float4 gt = (a.gate && r < a.R) ? *reinterpret_cast<const float4*>(a.gate + r * a.NOUT + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float gg[4] = {gt.x, gt.y, gt.z, gt.w}, rs[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
           const float bb[4] = {bias4.x, bias4.y, bias4.z, bias4.w}, ss[4] = {sc4.x, sc4.y, sc4.z, sc4.w},
                       hh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
 #pragma unroll
