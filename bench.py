@@ -327,6 +327,11 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         alg_bytes = (512.0 * N + 100.0) * B * T          # per rollout-kernel launch
+        # DRAM bytes of one launch from the committed `ncu --set full` capture of this exact config, else null
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", f"rollout_traffic_{a.kind}{N}_b{B}.json")
+        if os.path.exists(tpath):
+            traffic = float(json.load(open(tpath))["dram_bytes_per_launch"])
         achieved = alg_bytes / (roll_ms * 1e-3) / 1e9
         value = total_inst_steps / (elapsed_ms * 1e-3)
         line = {
@@ -347,7 +352,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": n_e2e},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_rollout (persistent decoder+env)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roll_ms},
         }
         if not a.no_cpu_baseline:
