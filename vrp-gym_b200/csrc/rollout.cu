@@ -42,7 +42,12 @@ struct RolloutParams {
   long long* prof;    // optional [8] cycle counters per phase (debug, vrpx_debug_rollout_profile)
 };
 
-constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_MMA;   // 16.5 + 128.5 + 72 KiB
+// Rollout tile: RMT x 16 instances.  With 16 instances per tile the working set that has to survive in L2 between the
+// glimpse passes and the pointer-logit pass (all CTAs x tile x 25.6 KB) halves to 60 MB.
+constexpr int RMT = 1;
+constexpr int RTM = 16 * RMT;
+constexpr size_t SMEM_X_MMA = smem_x_mma<RMT>(), SMEM_QC_MMA = smem_qc_mma<RMT>();
+constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_MMA;
 
 // Pull one instance's embeddings (N rows of 512 B) towards L2 ahead of their first use in a step: the first pass over
 // h would otherwise pay HBM latency on every row tile.
@@ -57,13 +62,13 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
   float* Xs = reinterpret_cast<float*>(smem_raw);
   float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA);
   float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA + SMEM_QC_MMA);
-  __shared__ float s_loadf[TM], s_lp[TM];
-  __shared__ int s_anyleft, s_act[TM];
+  __shared__ float s_loadf[RTM], s_lp[RTM];
+  __shared__ int s_anyleft, s_act[RTM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.env.N, kind = p.env.kind;
   const int64_t B = p.env.B;
-  const int64_t ntiles = (B + TM - 1) / TM;
+  const int64_t ntiles = (B + RTM - 1) / RTM;
   const float* __restrict__ h = p.h;
   unsigned bar_target = 0;
   long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -76,9 +81,9 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
 
   // ------------------------------------------------ prologue: Q~g[b] = A_g · mean_n h[b,n] + a_c
   for (int64_t tile = blockIdx.x; tile < ntiles && p.t0 == 0; tile += gridDim.x) {
-    const int64_t base = tile * TM;
-    const int cnt = (int)((B - base < TM) ? (B - base) : TM);
-    for (int m = warp; m < TM; m += NT / 32) {
+    const int64_t base = tile * RTM;
+    const int cnt = (int)((B - base < RTM) ? (B - base) : RTM);
+    for (int m = warp; m < RTM; m += NT / 32) {
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m < cnt) {
         const float4* hp = reinterpret_cast<const float4*>(h + (base + m) * N * E) + lane;
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = g;
     }
     __syncthreads();
-    tile_gemm_wide_mma(                                              // Q~g = A_g · g + a_c
+    tile_gemm_wide_mma<RMT>(                                              // Q~g = A_g · g + a_c
         Xs, p.w.ag_t, Wb, [&](int, int c) { return *reinterpret_cast<const float2*>(p.w.a_c + c); },
         [&](int m, int c, float v0, float v1) {
           if (m >= cnt) return;
@@ -108,13 +113,13 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
     const int trel = t - p.t0;
     bool cta_unfinished = false;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t base = tile * TM;
-      const int cnt = (int)((B - base < TM) ? (B - base) : TM);
+      const int64_t base = tile * RTM;
+      const int cnt = (int)((B - base < RTM) ? (B - base) : RTM);
       if (tid == 0) s_anyleft = 0;
       // ---------------- P0: gather last-node embeddings, vehicle load; pull this tile's Q~g rows towards L2
       for (int i = tid; i < cnt * 32; i += NT)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.qg + base * QW) + (size_t)i * 128));
-      for (int m = warp; m < TM; m += NT / 32) {
+      for (int m = warp; m < RTM; m += NT / 32) {
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < cnt && t > 0) {
           int last = p.env.cur[base + m];
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         }
       } else {
         if (t == 1 && kind != VRPX_IRP) {
-          tile_gemm_wide_mma(                                        // fold `first` (graph_decoder.py:111-113)
+          tile_gemm_wide_mma<RMT>(                                        // fold `first` (graph_decoder.py:111-113)
               Xs, p.w.af_t, Wb,
               [&](int m, int c) {
                 return (m < cnt) ? *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c) : make_float2(0.f, 0.f);
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
                 if (m < cnt) *reinterpret_cast<float2*>(p.qg + (base + m) * QW + c) = make_float2(v0, v1);
               });
         }
-        tile_gemm_wide_mma(                                          // q~ = Q~g (+ load · a_load) + A_l · h[last]
+        tile_gemm_wide_mma<RMT>(                                          // q~ = Q~g (+ load · a_load) + A_l · h[last]
             Xs, p.w.al_t, Wb,
             [&](int m, int c) {
               if (m >= cnt) return make_float2(0.f, 0.f);
@@ -329,12 +334,12 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           }
       }
       // rows >= cnt of C must be finite for GEMM-B (results unused): zero them
-      for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[(o >> 10) * QC_LD + (o & (QW - 1))] = 0.f;
+      for (int o = cnt * QW + tid; o < RTM * QW; o += NT) QC[(o >> 10) * QC_LD + (o & (QW - 1))] = 0.f;
       __syncthreads();
       VRPX_PROF(2)
 
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
-      tile_gemm_tall_mma(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
+      tile_gemm_tall_mma<RMT>(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
 
       VRPX_PROF(3)
       // ---------------- P4: logits, action, environment transition
@@ -546,7 +551,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
 
   VRPX_CUDA(cudaMemsetAsync(ws, 0, kRolloutSmall, stream));
   VRPX_CUDA(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-  int64_t ntiles = (env->B + TM - 1) / TM;
+  int64_t ntiles = (env->B + RTM - 1) / RTM;
   int grid = (int)((ntiles < (int64_t)num_sms()) ? ntiles : (int64_t)num_sms());
   void* args[] = {(void*)&p};
   VRPX_CUDA(cudaLaunchCooperativeKernel((void*)k_rollout, dim3(grid), dim3(NT), args, SMEM_TOTAL, stream));

@@ -218,8 +218,8 @@ constexpr int XS_LD = E + 4;        // 132: A fragments (row g, col t): bank (4g
 constexpr int QC_LD = QW + 4;       // 1028
 constexpr int WARP_LD = 64 + 8;     // 72: per-warp weight stage [8 k-rows][64 columns], B fragments (k = t, n = g): bank (8t + g) % 32
 constexpr int WARP_STAGE_FLOATS = 8 * WARP_LD;            // 576 floats = 2304 B: one mma k-step of a warp's 64 columns
-constexpr size_t SMEM_X_MMA = (size_t)TM * XS_LD * sizeof(float);
-constexpr size_t SMEM_QC_MMA = (size_t)TM * QC_LD * sizeof(float);
+template <int MT> constexpr size_t smem_x_mma() { return (size_t)(16 * MT) * XS_LD * sizeof(float); }
+template <int MT> constexpr size_t smem_qc_mma() { return (size_t)(16 * MT) * QC_LD * sizeof(float); }
 constexpr size_t SMEM_W_MMA = (size_t)(NT / 32) * 2 * WARP_STAGE_FLOATS * sizeof(float);   // 16 warps x 2 stages = 72 KiB
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
@@ -233,10 +233,11 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
 }
 
 // A fragments (hi and lo) of the two 16-row tiles for one k-step, from a row-major smem matrix with leading dim ld.
+template <int MT>
 __device__ __forceinline__ void load_a_frags(const float* __restrict__ A, int ld, int k0, int g, int t,
-                                             uint32_t (&ah)[2][4], uint32_t (&al)[2][4]) {
+                                             uint32_t (&ah)[MT][4], uint32_t (&al)[MT][4]) {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const float* r0 = A + (mt * 16 + g) * ld + k0 + t;
     const float* r1 = r0 + 8 * ld;
     split_tf32(r0[0], ah[mt][0], al[mt][0]);
@@ -258,8 +259,9 @@ __device__ __forceinline__ void stage_warp_kstep(const float* __restrict__ src, 
   }
 }
 
-// acc[2][8][4] += A[32][K = 8*nks] (smem, leading dim lda, k offset k_base) · W[k][64 columns of this warp]
-__device__ __forceinline__ void warp_gemm_mma(float (&acc)[2][8][4], const float* __restrict__ A, int lda, int k_base,
+// acc[MT][8][4] += A[16 MT][K = 8*nks] (smem, leading dim lda, k offset k_base) · W[k][64 columns of this warp]
+template <int MT>
+__device__ __forceinline__ void warp_gemm_mma(float (&acc)[MT][8][4], const float* __restrict__ A, int lda, int k_base,
                                               const float* __restrict__ wsrc, int wld, int nks, float* __restrict__ wbuf,
                                               int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -274,8 +276,8 @@ __device__ __forceinline__ void warp_gemm_mma(float (&acc)[2][8][4], const float
       cp_async_wait<0>();
     }
     __syncwarp();
-    uint32_t ah[2][4], al[2][4];
-    load_a_frags(A, lda, k_base + ks * 8, g, t, ah, al);
+    uint32_t ah[MT][4], al[MT][4];
+    load_a_frags<MT>(A, lda, k_base + ks * 8, g, t, ah, al);
     const float* wb = wbuf + (ks & 1) * WARP_STAGE_FLOATS + g;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -283,7 +285,7 @@ __device__ __forceinline__ void warp_gemm_mma(float (&acc)[2][8][4], const float
       split_tf32(wb[t * WARP_LD + 8 * j], bh0, bl0);
       split_tf32(wb[(t + 4) * WARP_LD + 8 * j], bh1, bl1);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         mma_tf32_16x8x8(acc[mt][j], al[mt], bh0, bh1);
         mma_tf32_16x8x8(acc[mt][j], ah[mt], bl0, bl1);
         mma_tf32_16x8x8(acc[mt][j], ah[mt], bh0, bh1);
@@ -296,22 +298,22 @@ __device__ __forceinline__ void warp_gemm_mma(float (&acc)[2][8][4], const float
 // out[32][1024] = init + Xs[32][128] (ld XS_LD) · Wt[128][1024].  Warp w owns columns [64w, 64w + 64).
 // init(m, c) -> float2 start value for (row m, columns c, c+1), fetched BEFORE the k loop so that its global-memory
 // latency hides behind the weight pipeline; epi(m, c, v0, v1) stores the result.
-template <class Init, class Epi>
+template <int MT, class Init, class Epi>
 __device__ __forceinline__ void tile_gemm_wide_mma(const float* __restrict__ Xs, const float* __restrict__ Wt,
                                                    float* __restrict__ Wb, Init init, Epi epi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  float acc[2][8][4];
+  float acc[MT][8][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = warp * 64 + 8 * j + 2 * t;
       const float2 i0 = init(mt * 16 + g, c), i1 = init(mt * 16 + g + 8, c);
       acc[mt][j][0] = i0.x; acc[mt][j][1] = i0.y; acc[mt][j][2] = i1.x; acc[mt][j][3] = i1.y;
     }
-  warp_gemm_mma(acc, Xs, XS_LD, 0, Wt + warp * 64, QW, 16, Wb + warp * 2 * WARP_STAGE_FLOATS, lane);
+  warp_gemm_mma<MT>(acc, Xs, XS_LD, 0, Wt + warp * 64, QW, 16, Wb + warp * 2 * WARP_STAGE_FLOATS, lane);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = warp * 64 + 8 * j + 2 * t;
@@ -323,34 +325,36 @@ __device__ __forceinline__ void tile_gemm_wide_mma(const float* __restrict__ Xs,
 // out[32][128] (ld out_ld) = Cs[32][1024] (ld QC_LD) · Mt[1024][128] + bias.  Warp (kg = w >> 1, ng = w & 1) owns
 // columns [64 ng, 64 ng + 64) over the k range [128 kg, 128 kg + 128); the 8 partial sums go through `part`
 // ([8][32][128] floats, may alias Cs).  The caller must have synchronised the CTA after writing Cs.
+template <int MT>
 __device__ __forceinline__ void tile_gemm_tall_mma(float* __restrict__ Cs, const float* __restrict__ Mt,
                                                    float* __restrict__ Wb, const float* __restrict__ bias,
                                                    float* __restrict__ part, float* __restrict__ out, int out_ld) {
+  constexpr int TMm = 16 * MT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int kg = warp >> 1, ng = warp & 1;
-  float acc[2][8][4];
+  float acc[MT][8][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
-  warp_gemm_mma(acc, Cs, QC_LD, kg * 128, Mt + (size_t)kg * 128 * E + ng * 64, E, 16, Wb + warp * 2 * WARP_STAGE_FLOATS,
-                lane);
+  warp_gemm_mma<MT>(acc, Cs, QC_LD, kg * 128, Mt + (size_t)kg * 128 * E + ng * 64, E, 16,
+                    Wb + warp * 2 * WARP_STAGE_FLOATS, lane);
   __syncthreads();  // every warp is done reading Cs before `part` (which may alias it) is written
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = ng * 64 + 8 * j + 2 * t;
-      *reinterpret_cast<float2*>(part + (kg * TM + mt * 16 + g) * E + c) = make_float2(acc[mt][j][0], acc[mt][j][1]);
-      *reinterpret_cast<float2*>(part + (kg * TM + mt * 16 + g + 8) * E + c) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+      *reinterpret_cast<float2*>(part + (kg * TMm + mt * 16 + g) * E + c) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+      *reinterpret_cast<float2*>(part + (kg * TMm + mt * 16 + g + 8) * E + c) = make_float2(acc[mt][j][2], acc[mt][j][3]);
     }
   __syncthreads();
-  for (int o = tid; o < TM * E; o += NT) {
+  for (int o = tid; o < TMm * E; o += NT) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += part[k * TM * E + o];
+    for (int k = 0; k < 8; ++k) s += part[k * TMm * E + o];
     out[(o >> 7) * out_ld + (o & (E - 1))] = s + (bias ? bias[o & (E - 1)] : 0.f);
   }
   __syncthreads();
