@@ -1,0 +1,42 @@
+"""The two caller scripts of the hot path run end to end on the GPU and keep the reference's file formats:
+reproduction CSV schema and a state_dict checkpoint that loads back."""
+import csv
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reproduction_script_csv(tmp_path):
+    out = tmp_path / "res.csv"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "vrp-gym_b200", "reproduction.py"), "--env_type", "VRP", "--num_nodes", "10",
+                           "--batch_size", "32", "--seeds", "1234", "--csv_path", str(out), "--model_path", "none"], cwd=tmp_path)
+    rows = list(csv.reader(open(out)))
+    assert rows[0] == ["Model", "Seed", "Mean Distance"] and len(rows) == 1 + 2 * 32
+    assert rows[1][0] == "VRP-Agent" and rows[2][0] == "VRP-Random-Agent"
+    assert all(float(r[2]) < 0 for r in rows[1:])  # rewards are negative tour lengths (tsp.py:98)
+
+
+def test_training_checkpoint_roundtrip(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "vrp-gym_b200"))
+    from agents import IRPAgent
+    from gym_vrp.envs import IRPEnv
+
+    env = IRPEnv(num_nodes=8, batch_size=64, num_draw=1, seed=5)
+    agent = IRPAgent(seed=5, csv_path=str(tmp_path / "log.csv"))
+    agent.train(env, epochs=2, check_point_dir=str(tmp_path) + "/")
+    agent.save_model(episode=50, check_point_dir=str(tmp_path) + "/")
+    sd = torch.load(tmp_path / "model_epoch_50.pt", map_location="cpu")
+    assert len(sd) == 69 and sd["decoder._context_proj.weight"].shape == (384, 257)
+    other = IRPAgent(seed=6)
+    other.model.load_state_dict(sd)
+    env2 = IRPEnv(num_nodes=8, batch_size=64, num_draw=1, seed=9)
+    from copy import deepcopy
+    a = agent.evaluate(deepcopy(env2))
+    b = other.evaluate(deepcopy(env2))
+    assert torch.allclose(a, b)
