@@ -73,3 +73,21 @@ def test_gemm_tc_in_place_residual():
                                           vrpx.ptr(h), 0, vrpx.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert (h.double() - ref).abs().max().item() <= 6e-5
+
+
+@pytest.mark.parametrize("R,M,N", [(5000, 128, 512), (33000, 384, 128), (777, 512, 128), (4097, 128, 1024), (1000, 128, 4)])
+def test_gemm_tn_accumulate(R, M, N):
+    """Weight-gradient reduction C[M][N] += A^T · B (tensor-pipe kernel for 64-multiples, SIMT otherwise)."""
+    import vrpx
+
+    dev = vrpx.require_device()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    A = torch.randn(R, M, generator=g).to(dev)
+    Bm = torch.randn(R, N, generator=g).to(dev)
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    C = C0.clone()
+    vrpx.check(vrpx.lib().vrpx_gemm_tn_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(C), R, M, N, vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double().T @ Bm.double()
+    err = (C.double() - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item() + 1e-5, (R, M, N, err)

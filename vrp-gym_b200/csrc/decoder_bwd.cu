@@ -551,6 +551,96 @@ __global__ void __launch_bounds__(256) k_gemm_tn_atomic(const float* __restrict_
   }
 }
 
+// Tensor-pipe version of the same reduction GEMM for M, N multiples of 64: C[M][N] += A^T · Bm on mma.sync.m16n8k8 TF32
+// with the 3-term split.  CTA = 4 warps, 64 x 64 output tile; warp w owns rows [16w, 16w+16) x 64 columns; the row
+// (reduction) dimension is streamed in 32-row chunks through a cp.async double buffer.
+//   A fragment (m = g / g+8, k = t / t+4)  = A[r0 + t (+4)][m0 + g (+8)]   (rows of As are reduction rows)
+//   B fragment (k = t / t+4, n = g)        = Bm[r0 + t (+4)][n0 + g]
+constexpr int TN_LD = 64 + 8;   // (8t + g) % 32 distinct banks for both fragment patterns
+
+__device__ __forceinline__ void tn_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void tn_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) k_gemm_tn_mma(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                      float* __restrict__ C, int64_t R, int M, int N,
+                                                      int64_t rows_per_cta) {
+  __shared__ __align__(16) float As[2][32][TN_LD], Bs[2][32][TN_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.z * 64;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = (r_begin + rows_per_cta < R) ? r_begin + rows_per_cta : R;
+  const int nchunks = (int)((r_end - r_begin + 31) / 32);
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+  auto stage = [&](int ch, int buf) {
+    const int64_t r0 = r_begin + (int64_t)ch * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 128 * i;          // 32 rows x 16 float4
+      const int rr = idx >> 4, c4 = (idx & 15) * 4;
+      float* da = &As[buf][rr][c4];
+      float* db = &Bs[buf][rr][c4];
+      if (r0 + rr < r_end) {
+        unsigned sa = (unsigned)__cvta_generic_to_shared(da), sb = (unsigned)__cvta_generic_to_shared(db);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(A + (r0 + rr) * M + m0 + c4) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb), "l"(Bm + (r0 + rr) * N + n0 + c4) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(db) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (nchunks > 0) stage(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) {
+      stage(ch + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+      const float* ap = &As[buf][ks * 8 + t][warp * 16 + g];
+      tn_split(ap[0], ah[0], al[0]);               // (m = g,   k = t)
+      tn_split(ap[8], ah[1], al[1]);               // (m = g+8, k = t)
+      tn_split(ap[4 * TN_LD], ah[2], al[2]);       // (m = g,   k = t+4)
+      tn_split(ap[4 * TN_LD + 8], ah[3], al[3]);   // (m = g+8, k = t+4)
+      const float* bp = &Bs[buf][ks * 8 + t][g];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t bh0, bl0, bh1, bl1;
+        tn_split(bp[8 * j], bh0, bl0);
+        tn_split(bp[4 * TN_LD + 8 * j], bh1, bl1);
+        tn_mma(acc[j], al, bh0, bh1);
+        tn_mma(acc[j], ah, bl0, bl1);
+        tn_mma(acc[j], ah, bh0, bh1);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = n0 + 8 * j + 2 * t;
+    float* c0 = C + (size_t)(m0 + warp * 16 + g) * N + n;
+    float* c1 = C + (size_t)(m0 + warp * 16 + g + 8) * N + n;
+    atomicAdd(c0, acc[j][0]); atomicAdd(c0 + 1, acc[j][1]);
+    atomicAdd(c1, acc[j][2]); atomicAdd(c1 + 1, acc[j][3]);
+  }
+}
+
 // out[c] += sum_r X[r][c]   (C <= 1024 columns, any R)
 __global__ void __launch_bounds__(256) k_colsum_atomic(const float* __restrict__ X, int64_t R, int Ccols,
                                                         float* __restrict__ out, int64_t rows_per_cta) {
@@ -649,7 +739,13 @@ int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R
   int64_t rows = ((R + ctas - 1) / ctas + 15) / 16 * 16;
   ctas = (R + rows - 1) / rows;
   dim3 grid((unsigned)ctas, (unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
-  k_gemm_tn_atomic<<<grid, 256, 0, (cudaStream_t)stream>>>(A, Bm, C, R, M, N, rows);
+  if (M % 64 == 0 && N % 64 == 0) {
+    rows = (rows + 31) / 32 * 32;
+    grid.x = (unsigned)((R + rows - 1) / rows);
+    k_gemm_tn_mma<<<grid, 128, 0, (cudaStream_t)stream>>>(A, Bm, C, R, M, N, rows);
+  } else {
+    k_gemm_tn_atomic<<<grid, 256, 0, (cudaStream_t)stream>>>(A, Bm, C, R, M, N, rows);
+  }
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }
