@@ -33,19 +33,25 @@ struct DecBwdParams {
   float* scratch;  // [grid][TM][3][1024]: q~ | p[n][8] | dz[128], q^[128]
 };
 
-constexpr size_t BWD_SMEM = SMEM_X + SMEM_QC + SMEM_W + SMEM_X;  // Xs | QC | Wb | DQ  = 224 KiB
+// Xs | QC | Wb | DQ with the padded leading dimensions of the tensor-pipe tile GEMMs (XS_LD, QC_LD): 225.5 KiB
+constexpr size_t BWD_X = (size_t)TM * XS_LD * sizeof(float), BWD_QC = (size_t)TM * QC_LD * sizeof(float);
+constexpr size_t BWD_SMEM = BWD_X + BWD_QC + SMEM_W + BWD_X;
 
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
 
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Xs = reinterpret_cast<float*>(smem_raw);
-  float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X);
-  float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X + SMEM_QC);
-  float* DQ = reinterpret_cast<float*>(smem_raw + SMEM_X + SMEM_QC + SMEM_W);
+  float* QC = reinterpret_cast<float*>(smem_raw + BWD_X);
+  float* Wb = reinterpret_cast<float*>(smem_raw + BWD_X + BWD_QC);
+  float* DQ = reinterpret_cast<float*>(smem_raw + BWD_X + BWD_QC + SMEM_W);
   __shared__ float s_loadf[TM], s_w[TM];
   __shared__ int s_act[TM], s_prev[TM], s_live[TM], s_anylive;
 
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
           for (int i = 0; i < 4; ++i) free_cnt += __popc(~__shfl_sync(0xffffffffu, mw, i) & full_bits(N).w[i]);
           live = (w != 0.f && free_cnt > 1) ? 1 : 0;
         }
-        *reinterpret_cast<float4*>(Xs + m * E + lane * 4) = xv;
+        *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = xv;
         if (lane == 0) {
           s_loadf[m] = lf; s_w[m] = w; s_act[m] = act; s_prev[m] = prev; s_live[m] = live;
           if (live) s_anylive = 1;
@@ -102,27 +108,31 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
           int m = o >> 10, c = o & (QW - 1);
           float y = p.qg0[(base + m) * QW + c] + p.a_q0[c];
           if (kind == VRPX_IRP) y = fmaf(s_loadf[m], p.a_load[c], y);
-          QC[o] = y;
+          QC[m * QC_LD + c] = y;
         }
       } else {
-        tile_gemm_wide(Xs, p.al_t, Wb, [&](int m, int c, float4 v) {
-          if (m >= cnt) return;
-          const float4 q = *reinterpret_cast<const float4*>(p.qg + (base + m) * QW + c);
-          v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
-          if (kind == VRPX_IRP) {
-            const float4 al = *reinterpret_cast<const float4*>(p.a_load + c);
-            const float lf = s_loadf[m];
-            v = make_float4(fmaf(lf, al.x, v.x), fmaf(lf, al.y, v.y), fmaf(lf, al.z, v.z), fmaf(lf, al.w, v.w));
-          }
-          *reinterpret_cast<float4*>(QC + m * QW + c) = v;
-        });
+        tile_gemm_wide_mma_sw<2>(
+            Xs, XS_LD, p.al_t, Wb,
+            [&](int m, int c) -> float2 {
+              if (m >= cnt) return make_float2(0.f, 0.f);
+              float2 q = *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c);
+              if (kind == VRPX_IRP) {
+                const float2 al = *reinterpret_cast<const float2*>(p.a_load + c);
+                const float lf = s_loadf[m];
+                q = make_float2(fmaf(lf, al.x, q.x), fmaf(lf, al.y, q.y));
+              }
+              return q;
+            },
+            [&](int m, int c, float v0, float v1) {
+              if (m < cnt) *reinterpret_cast<float2*>(QC + m * QC_LD + c) = make_float2(v0, v1);
+            });
       }
       __syncthreads();
 
       // ---------------- B2: glimpse forward (scores, p, c); q~ and p are parked in the per-CTA scratch
       for (int m = warp; m < cnt; m += NT / 32) {
         const int64_t b = base + m;
-        float* slot = QC + m * QW;
+        float* slot = QC + m * QC_LD;
         float* sc_q = SC + (size_t)m * 3 * QW;
         float* sc_p = sc_q + QW;
         float4 qt[NH];
@@ -214,17 +224,17 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) *reinterpret_cast<float4*>(slot + hh * E + lane * 4) = c[hh];
       }
-      for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[o] = 0.f;
+      for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[(o >> 10) * QC_LD + (o & (QW - 1))] = 0.f;
       __syncthreads();
 
       // ---------------- B3: q^ = C · M^T + m_c -> DQ   (partials go through Wb: QC must keep c for the dM update)
-      tile_gemm_tall(QC, p.m_t, Wb, p.m_c, Wb, DQ);   // NOTE: `part` aliases the weight stage, see below
+      tile_gemm_tall_mma_sw<2>(QC, QC_LD, p.m_t, Wb, p.m_c, Wb, DQ, XS_LD);   // `part` aliases the weight stage
       // ---------------- B4: pointer logits forward + backward: dz, dq^ (-> DQ), dz kept in su for B7
       for (int m = warp; m < TM; m += NT / 32) {
         float4 dqh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < cnt && s_live[m]) {
           const int64_t b = base + m;
-          const float4 qh = *reinterpret_cast<const float4*>(DQ + m * E + lane * 4);
+          const float4 qh = *reinterpret_cast<const float4*>(DQ + m * XS_LD + lane * 4);
           const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
           for (int n0 = 0; n0 < N; n0 += 8) {
             float v[8];
@@ -284,50 +294,72 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
         }
         __syncwarp();
         // every row of DQ must hold dq^ (zeros for idle instances) for the GEMMs below
-        *reinterpret_cast<float4*>(DQ + m * E + lane * 4) = dqh;
+        *reinterpret_cast<float4*>(DQ + m * XS_LD + lane * 4) = dqh;
       }
       __syncthreads();
       if (tid < E) {
         float s = 0.f;
-        for (int m = 0; m < cnt; ++m) s += DQ[m * E + tid];
+        for (int m = 0; m < cnt; ++m) s += DQ[m * XS_LD + tid];
         mc_acc += s;
       }
 
       // ---------------- B5: d m_t[k][e] += sum_m c[m][k] dq^[m][e]     (1024 x 128 outputs, K = 32)
+      // Tensor pipe: A fragment (row k, col m) = c[m][k] read from QC, B fragment (row m, col e) = dq^[m][e] from DQ;
+      // warp w owns rows [64w, 64w + 64) of d m_t.
       {
-        const int tx = tid & 31, ty = tid >> 5;  // 16 k-groups of 64 rows, 4 columns per thread
-        for (int pass = 0; pass < 8; ++pass) {
-          const int k0 = ty * 64 + pass * 8;
-          float acc[8][4];
+        const int g = lane >> 2, t4 = lane & 3;
+        for (int mt = 0; mt < 4; ++mt) {
+          const int k0 = warp * 64 + mt * 16;
+          uint32_t ah[TM / 8][4], al[TM / 8][4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-          for (int m = 0; m < cnt; ++m) {
-            const float4 c0 = *reinterpret_cast<const float4*>(QC + m * QW + k0);
-            const float4 c1 = *reinterpret_cast<const float4*>(QC + m * QW + k0 + 4);
-            const float4 d = *reinterpret_cast<const float4*>(DQ + m * E + tx * 4);
-            const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              acc[i][0] = fmaf(cv[i], d.x, acc[i][0]); acc[i][1] = fmaf(cv[i], d.y, acc[i][1]);
-              acc[i][2] = fmaf(cv[i], d.z, acc[i][2]); acc[i][3] = fmaf(cv[i], d.w, acc[i][3]);
-            }
+          for (int ks = 0; ks < TM / 8; ++ks) {
+            const float* r0 = QC + (ks * 8 + t4) * QC_LD + k0 + g;
+            const float* r1 = r0 + 4 * QC_LD;
+            split_tf32(r0[0], ah[ks][0], al[ks][0]);
+            split_tf32(r0[8], ah[ks][1], al[ks][1]);
+            split_tf32(r1[0], ah[ks][2], al[ks][2]);
+            split_tf32(r1[8], ah[ks][3], al[ks][3]);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            red_add4(p.d_m_t + (size_t)(k0 + i) * E + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+          for (int nh = 0; nh < 2; ++nh) {
+            float acc[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < TM / 8; ++ks) {
+              const float* b0p = DQ + (ks * 8 + t4) * XS_LD + nh * 64 + g;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(b0p[8 * j], bh0, bl0);
+                split_tf32(b0p[4 * XS_LD + 8 * j], bh1, bl1);
+                mma_tf32_16x8x8(acc[j], al[ks], bh0, bh1);
+                mma_tf32_16x8x8(acc[j], ah[ks], bl0, bl1);
+                mma_tf32_16x8x8(acc[j], ah[ks], bh0, bh1);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float* dst = p.d_m_t + (size_t)(k0 + g) * E + nh * 64 + 8 * j + 2 * t4;
+              red_add2(dst, acc[j][0], acc[j][1]);
+              red_add2(dst + 8 * E, acc[j][2], acc[j][3]);
+            }
+          }
         }
       }
       __syncthreads();
 
       // ---------------- B6: dc = dq^ · M  -> QC (c is dead now)
-      tile_gemm_wide(DQ, p.m_n, Wb, [&](int m, int c, float4 v) { *reinterpret_cast<float4*>(QC + m * QW + c) = v; });
+      tile_gemm_wide_mma_sw<2>(
+          DQ, XS_LD, p.m_n, Wb, [](int, int) -> float2 { return make_float2(0.f, 0.f); },
+          [&](int m, int c, float v0, float v1) { *reinterpret_cast<float2*>(QC + m * QC_LD + c) = make_float2(v0, v1); });
       __syncthreads();
 
       // ---------------- B7: glimpse backward per instance: dp, ds, dq~ (-> QC slot), dH += ...
       for (int m = warp; m < TM; m += NT / 32) {
-        float* slot = QC + m * QW;
+        float* slot = QC + m * QC_LD;
         float4 dq[NH];
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) dq[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -458,39 +490,53 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
 
       if (t > 0) {
         // ---------------- B8: d al_t[j][c] += sum_m x_l[m][j] dq~[m][c]     (128 x 1024 outputs, K = 32)
+        // Tensor pipe: A fragment (row j, col m) = x_l[m][j] from Xs, B fragment (row m, col c) = dq~[m][c] from QC;
+        // warp w owns columns [64w, 64w + 64) of d al_t, looping over the eight 16-row j tiles.
         {
-          const int tx = tid & 127, ty = tid >> 7;  // 4 j-groups of 32 rows, 4 columns per thread per half
-          for (int pass = 0; pass < 8; ++pass) {
-            const int j0 = ty * 32 + (pass >> 1) * 8, c0 = (pass & 1) * 512 + tx * 4;
+          const int g = lane >> 2, t4 = lane & 3;
+          for (int mt = 0; mt < 8; ++mt) {
+            const int j0 = mt * 16;
             float acc[8][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-            for (int m = 0; m < cnt; ++m) {
-              const float4 x0 = *reinterpret_cast<const float4*>(Xs + m * E + j0);
-              const float4 x1 = *reinterpret_cast<const float4*>(Xs + m * E + j0 + 4);
-              const float4 d = *reinterpret_cast<const float4*>(QC + m * QW + c0);
-              const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+              for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                acc[i][0] = fmaf(xv[i], d.x, acc[i][0]); acc[i][1] = fmaf(xv[i], d.y, acc[i][1]);
-                acc[i][2] = fmaf(xv[i], d.z, acc[i][2]); acc[i][3] = fmaf(xv[i], d.w, acc[i][3]);
+            for (int ks = 0; ks < TM / 8; ++ks) {
+              uint32_t ah[4], al[4];
+              const float* r0 = Xs + (ks * 8 + t4) * XS_LD + j0 + g;
+              const float* r1 = r0 + 4 * XS_LD;
+              split_tf32(r0[0], ah[0], al[0]);
+              split_tf32(r0[8], ah[1], al[1]);
+              split_tf32(r1[0], ah[2], al[2]);
+              split_tf32(r1[8], ah[3], al[3]);
+              const float* b0p = QC + (ks * 8 + t4) * QC_LD + warp * 64 + g;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(b0p[8 * j], bh0, bl0);
+                split_tf32(b0p[4 * QC_LD + 8 * j], bh1, bl1);
+                mma_tf32_16x8x8(acc[j], al, bh0, bh1);
+                mma_tf32_16x8x8(acc[j], ah, bl0, bl1);
+                mma_tf32_16x8x8(acc[j], ah, bh0, bh1);
               }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              red_add4(p.d_al_t + (size_t)(j0 + i) * QW + c0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            for (int j = 0; j < 8; ++j) {
+              float* dst = p.d_al_t + (size_t)(j0 + g) * QW + warp * 64 + 8 * j + 2 * t4;
+              red_add2(dst, acc[j][0], acc[j][1]);
+              red_add2(dst + 8 * QW, acc[j][2], acc[j][3]);
+            }
           }
         }
         __syncthreads();
         // ---------------- B9: dx_l = dq~ · A_l -> DQ, then dH[b, last] += dx_l
-        tile_gemm_tall(QC, p.al_n, Wb, nullptr, Wb, DQ);
+        tile_gemm_tall_mma_sw<2>(QC, QC_LD, p.al_n, Wb, nullptr, Wb, DQ, XS_LD);
         for (int m = warp; m < cnt; m += NT / 32) {
           if (!s_live[m]) continue;
           const int64_t b = base + m;
           float4* dhp = reinterpret_cast<float4*>(p.dH + (b * N + s_prev[m]) * E) + lane;
-          const float4 g = *reinterpret_cast<const float4*>(DQ + m * E + lane * 4);
+          const float4 g = *reinterpret_cast<const float4*>(DQ + m * XS_LD + lane * 4);
           float4 o = *dhp;
           *dhp = make_float4(o.x + g.x, o.y + g.y, o.z + g.z, o.w + g.w);
         }

@@ -360,4 +360,118 @@ __device__ __forceinline__ void tile_gemm_tall_mma(float* __restrict__ Cs, const
   __syncthreads();
 }
 
+// ---------------------------------------------------------------- swizzled-stage variants (decoder backward)
+// Same tensor-pipe tile GEMMs with an UNPADDED per-warp weight stage [8 k-rows][NC = 8 NJ columns]: the 16-byte chunks of
+// row r are stored at column c ^ ((r & 3) << 3), which makes the B-fragment reads (k = t, n = g) conflict free without
+// the 8-float row padding — the stages of 16 warps then fit the backward kernel's 64 KiB weight buffer.
+template <int NJ>
+__device__ __forceinline__ void stage_warp_kstep_sw(const float* __restrict__ src, int ld, int kstep,
+                                                    float* __restrict__ dst, int lane) {
+  constexpr int NC = 8 * NJ, F4 = NC / 4;
+#pragma unroll
+  for (int i = 0; i < (8 * F4) / 32; ++i) {
+    const int idx = lane + 32 * i;
+    const int r = idx / F4, c4 = idx % F4;
+    cp_async16(dst + r * NC + ((c4 * 4) ^ ((r & 3) << 3)), src + (size_t)(kstep * 8 + r) * ld + c4 * 4);
+  }
+}
+
+template <int MT, int NJ>
+__device__ __forceinline__ void warp_gemm_mma_sw(float (&acc)[MT][NJ][4], const float* __restrict__ A, int lda, int k_base,
+                                                 const float* __restrict__ wsrc, int wld, int nks,
+                                                 float* __restrict__ wbuf, int lane) {
+  constexpr int NC = 8 * NJ, STAGE = 8 * NC;
+  const int g = lane >> 2, t = lane & 3;
+  stage_warp_kstep_sw<NJ>(wsrc, wld, 0, wbuf, lane);
+  cp_async_commit();
+  for (int ks = 0; ks < nks; ++ks) {
+    if (ks + 1 < nks) {
+      stage_warp_kstep_sw<NJ>(wsrc, wld, ks + 1, wbuf + ((ks + 1) & 1) * STAGE, lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    uint32_t ah[MT][4], al[MT][4];
+    load_a_frags<MT>(A, lda, k_base + ks * 8, g, t, ah, al);
+    const float* wb = wbuf + (ks & 1) * STAGE;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = (8 * j + g) ^ (t << 3);
+      uint32_t bh0, bl0, bh1, bl1;
+      split_tf32(wb[t * NC + c], bh0, bl0);
+      split_tf32(wb[(t + 4) * NC + c], bh1, bl1);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        mma_tf32_16x8x8(acc[mt][j], al[mt], bh0, bh1);
+        mma_tf32_16x8x8(acc[mt][j], ah[mt], bl0, bl1);
+        mma_tf32_16x8x8(acc[mt][j], ah[mt], bh0, bh1);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// out[16 MT][1024] = init + Xs[16 MT][128] (ld lda) · Wt[128][1024]; warp w owns columns [64w, 64w + 64).
+// Wb: 16 warps x 2 stages x 512 floats = 64 KiB.
+template <int MT, class Init, class Epi>
+__device__ __forceinline__ void tile_gemm_wide_mma_sw(const float* __restrict__ Xs, int lda, const float* __restrict__ Wt,
+                                                      float* __restrict__ Wb, Init init, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[MT][8][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = warp * 64 + 8 * j + 2 * t;
+      const float2 i0 = init(mt * 16 + g, c), i1 = init(mt * 16 + g + 8, c);
+      acc[mt][j][0] = i0.x; acc[mt][j][1] = i0.y; acc[mt][j][2] = i1.x; acc[mt][j][3] = i1.y;
+    }
+  warp_gemm_mma_sw<MT, 8>(acc, Xs, lda, 0, Wt + warp * 64, QW, 16, Wb + warp * 2 * 512, lane);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = warp * 64 + 8 * j + 2 * t;
+      epi(mt * 16 + g, c, acc[mt][j][0], acc[mt][j][1]);
+      epi(mt * 16 + g + 8, c, acc[mt][j][2], acc[mt][j][3]);
+    }
+}
+
+// out[16 MT][128] (ld out_ld) = Cs[16 MT][1024] (ld ldc) · Mt[1024][128] + bias.  Warp (kg = w >> 2, ng = w & 3) owns
+// columns [32 ng, 32 ng + 32) over the k range [256 kg, 256 kg + 256); the 4 partial sums go through `part`
+// ([4][16 MT][128] floats = 64 KiB at MT = 2; may alias Wb — it is written only after every warp has left the k loop).
+template <int MT>
+__device__ __forceinline__ void tile_gemm_tall_mma_sw(const float* __restrict__ Cs, int ldc, const float* __restrict__ Mt,
+                                                      float* __restrict__ Wb, const float* __restrict__ bias,
+                                                      float* __restrict__ part, float* __restrict__ out, int out_ld) {
+  constexpr int TMm = 16 * MT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int kg = warp >> 2, ng = warp & 3;
+  float acc[MT][4][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+  warp_gemm_mma_sw<MT, 4>(acc, Cs, ldc, kg * 256, Mt + (size_t)kg * 256 * E + ng * 32, E, 32, Wb + warp * 2 * 256, lane);
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ng * 32 + 8 * j + 2 * t;
+      *reinterpret_cast<float2*>(part + (kg * TMm + mt * 16 + g) * E + c) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+      *reinterpret_cast<float2*>(part + (kg * TMm + mt * 16 + g + 8) * E + c) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+    }
+  __syncthreads();
+  for (int o = tid; o < TMm * E; o += NT) {
+    const float s = (part[o] + part[TMm * E + o]) + (part[2 * TMm * E + o] + part[3 * TMm * E + o]);
+    out[(o >> 7) * out_ld + (o & (E - 1))] = s + (bias ? bias[o & (E - 1)] : 0.f);
+  }
+  __syncthreads();
+}
+
 }  // namespace vrpx
