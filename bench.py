@@ -290,7 +290,7 @@ def main():
     dem_h = torch.from_numpy(s.get_demands()[:, :, 0]).pin_memory()
 
     def e2e_step():
-        e = Env.from_arrays(xy_h.numpy(), dep_h.numpy(), dem_h.numpy() if a.kind == "irp" else None, device=dev)
+        e = Env.from_arrays(xy_h.numpy(), dep_h.numpy(), dem_h.numpy() if a.kind != "tsp" else None, device=dev)
         loss = agent.evaluate(e)
         return loss.cpu(), e.step_count
 
@@ -307,7 +307,7 @@ def main():
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
-    h2d = int(xy_h.numel() * 8 + dep_h.numel() * 4 + dem_h.numel() * 8)
+    h2d = int(xy_h.numel() * 8 + dep_h.numel() * 4 + (dem_h.numel() * 8 if a.kind != "tsp" else 0))
     d2h = int(B * 4)
 
     # ---- max over ranks

@@ -64,7 +64,10 @@ class TSPEnv:
     # ------------------------------------------------------------------ construction helpers
     @classmethod
     def from_arrays(cls, xy, depots, demand=None, num_draw: int = 0, *, device=None):
-        """Build an environment around given instances (host arrays): xy (B,N,2) f64, depots (B,), demand (B,N)."""
+        """Build an environment around given instances (host arrays): xy (B,N,2) f64, depots (B,), demand (B,N).
+
+        Contiguous float64 arrays are ADOPTED as the host-side instance store (no host copy) and uploaded straight from
+        the caller's memory; when that memory is pinned the upload is an asynchronous DMA on the current stream."""
         xy = np.ascontiguousarray(xy, dtype=np.float64)
         B, N, _ = xy.shape
         self = cls.__new__(cls)
@@ -75,14 +78,14 @@ class TSPEnv:
         self.draw_idxs = np.arange(num_draw)
         self.video_save_path = None
         net = VRPNetwork(B, N, 1, plot_demand=cls._PLOT_DEMAND, _sample=False)
-        net._store.xy[:] = xy
-        net._store.depots[:, 0] = np.asarray(depots).reshape(B)
+        net._store.xy = xy
+        net._store.depots = np.asarray(depots).reshape(B, 1).astype(int)
         if demand is not None:
-            net._store.demand[:] = np.asarray(demand, dtype=np.float64).reshape(B, N)
+            net._store.demand = np.ascontiguousarray(demand, dtype=np.float64).reshape(B, N)
         self._sampler = net
         self._sampler_stale = False
         self._alloc_state()
-        self._upload_instances()
+        self._upload_instances(with_demand=demand is not None)
         self._reset_episode()
         return self
 
@@ -116,11 +119,14 @@ class TSPEnv:
         self._load = torch.ones((B,), dtype=torch.float64, device=dev)
         self._host_cur = None
 
-    def _upload_instances(self):
+    def _upload_instances(self, with_demand: bool = True):
         s = self._sampler._store
-        self._xy.copy_(torch.from_numpy(s.xy))
+        self._xy.copy_(torch.from_numpy(s.xy), non_blocking=True)
         self._depot.copy_(torch.from_numpy(s.depots[:, 0].astype(np.int32)))
-        self._demand.copy_(torch.from_numpy(s.demand))
+        if with_demand:
+            self._demand.copy_(torch.from_numpy(s.demand), non_blocking=True)
+        else:
+            self._demand.zero_()
         self._uploaded_version = self._sampler.version
 
     def _sync_instances(self):
