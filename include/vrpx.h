@@ -25,7 +25,7 @@ extern "C" {
 #define VRPX_API
 #endif
 
-#define VRPX_ABI_VERSION 1
+#define VRPX_ABI_VERSION 2
 #define VRPX_MAX_NODES 128 /* visited bitmask = 4 x u32 per instance */
 #define VRPX_EMB 128       /* embedding width E (graph_tsp_agent.py:98) */
 #define VRPX_HEADS 8       /* heads (graph_tsp_agent.py:101, :55) */
@@ -174,10 +174,16 @@ VRPX_API int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_enc
  *   a_load[1024]       IRP only: Kd · W_q · W_ctx[:, 256]   (multiplied by the f32 vehicle load)
  *   m_t   [1024][128]  row h*128+d: (W_kp^T · W_ao · W_o[:, head h] · W_v,h)[:, d] / sqrt(128)
  *   m_c   [128]        W_kp^T · W_ao · (W_o · b_v + b_o) / sqrt(128)
+ *   qk_w  [768][128]   optional (may be NULL): rows 0..383 = W_q[:, last block] / sqrt(48) (IRP: W_q · W_ctx), rows
+ *                      384..767 = W_k — the rank-48 factors of al_t per head.  With it (and the larger workspace of
+ *                      vrpx_rollout_table_workspace_bytes) vrpx_rollout builds, once per episode, the score table
+ *                      S1[b][l][head][n] = (A_l h[b,l])_head · h[b,n] and the decode steps t >= 2 read their glimpse
+ *                      scores from it instead of recomputing A_l · h[last] and the score pass every step.
  * The key bias b_k shifts every score of a head equally and cancels in the softmax. */
 typedef struct vrpx_decoder_weights {
   const float *ag_t, *af_t, *al_t, *a_c, *a_q0, *a_load;
   const float *m_t, *m_c;
+  const float *qk_w;
 } vrpx_decoder_weights;
 
 /* Optional per-step history written by vrpx_rollout for the recompute-based backward (any field may be NULL). */
@@ -190,6 +196,9 @@ typedef struct vrpx_rollout_trace {
 typedef enum vrpx_rollout_mode { VRPX_GREEDY = 0, VRPX_SAMPLE = 1, VRPX_TEACHER = 2 } vrpx_rollout_mode;
 
 VRPX_API int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N);
+/* Workspace size that additionally holds the per-episode glimpse score tables (see qk_w above).  A whole-episode call
+ * (t_begin == 0, Tmax >= 3) given at least this much workspace and a non-NULL qk_w runs in table mode. */
+VRPX_API int64_t vrpx_rollout_table_workspace_bytes(int32_t kind, int64_t B, int32_t N);
 
 /* The rollout loop TSPModel/VRPModel/IRPModel.forward (agents/graph_tsp_agent.py:78-92,
  * graph_vrp_agent.py:69-83, graph_irp_agent.py:82-105) with GraphDecoder.forward

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14, names
     for n in names:
         assert hasattr(L, n), f"libvrpx.so does not export {n}"
-    assert L.vrpx_abi_version() == 1
+    assert L.vrpx_abi_version() == 2
     assert L.vrpx_launch_count() == 0
 
 

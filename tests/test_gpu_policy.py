@@ -30,10 +30,12 @@ def _rel(got, ref):
     return float((np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)).max())
 
 
+@pytest.mark.parametrize("score_tables", [True, False], ids=["tables", "classic"])
 @pytest.mark.parametrize("gemm_path", [1, 0], ids=["simt", "tcgen05"])
 @pytest.mark.parametrize("kind", ["tsp", "vrp", "irp"])
-def test_teacher_forced_logits_and_embeddings(golden_dir, kind, gemm_path):
-    """Replay the reference's greedy tape: per-step masked pointer logits, embeddings and costs match."""
+def test_teacher_forced_logits_and_embeddings(golden_dir, kind, gemm_path, score_tables):
+    """Replay the reference's greedy tape: per-step masked pointer logits, embeddings and costs match — with the
+    per-episode glimpse score tables (default) and with the classic per-step score pass."""
     z = _load(golden_dir, kind)
     Env, Agent = _cls(kind)
     for N, B, seed in CASES:
@@ -42,6 +44,7 @@ def test_teacher_forced_logits_and_embeddings(golden_dir, kind, gemm_path):
         agent = Agent(seed=seed)
         agent.model.eval()
         agent.model.encoder.gemm_path = gemm_path
+        agent.model.decoder.score_tables = score_tables
         tape = z[key + "/greedy_actions"]
         with torch.no_grad():
             loss, logp = agent.model(env, rollout=True, tape=tape, want_logits=True)
@@ -212,3 +215,27 @@ def test_sampling_distribution_and_determinism():
     assert chi2 < 40, (chi2, emp, p)  # 8 dof; P(chi2 > 40) ~ 3e-6
     assert emp[0] == 0  # the depot is masked
     assert np.isfinite(logp.cpu().numpy()).all() and (logp <= 0).all()
+
+
+@pytest.mark.parametrize("kind,N,B", [("tsp", 50, 777), ("vrp", 21, 300), ("irp", 100, 130), ("tsp", 128, 40)])
+def test_score_table_mode_matches_classic(kind, N, B):
+    """Table mode (S1/S0 gathered per step) and the classic mode (GEMM-A + score pass every step) are two evaluation
+    orders of the same scores: on a teacher-forced tape all masked logits agree to 1e-5 (relative, floor 1)."""
+    Env, Agent = _cls(kind)
+    agent = Agent(seed=5)
+    agent.model.eval()
+    env = Env(N, B, 0, seed=11, instance_rng="philox")
+    agent.model.decoder.score_tables = False
+    with torch.no_grad():
+        loss0, _ = agent.model(env, rollout=True, want_logits=True)
+    out0 = agent.model.last_rollout
+    tape, ref = out0["tape"].cpu().numpy(), out0["logits"].cpu().numpy()
+    env.restart_episode()
+    agent.model.decoder.score_tables = True
+    with torch.no_grad():
+        loss1, _ = agent.model(env, rollout=True, tape=tape, want_logits=True)
+    got = agent.model.last_rollout["logits"].cpu().numpy()
+    fin = np.isfinite(ref)
+    assert np.array_equal(fin, np.isfinite(got))
+    assert _rel(got[fin], ref[fin]) < 1e-5
+    assert _rel(loss1.cpu().numpy(), loss0.cpu().numpy()) < 1e-5

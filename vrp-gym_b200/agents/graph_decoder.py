@@ -41,6 +41,7 @@ class GraphDecoder(nn.Module):
         self.num_heads = num_heads
         self._packed = {False: packing.PackedDecoder(), True: packing.PackedDecoder()}
         self._ep = None  # single-step decoding state
+        self.score_tables = True  # whole-episode rollouts precompute the glimpse score tables (False: classic kernel path)
 
     # ------------------------------------------------------------------ whole-episode entry (used by the models)
     def packed(self, irp: bool, device) -> "vrpx.DecoderWeights":
@@ -70,7 +71,16 @@ class GraphDecoder(nn.Module):
         logits = torch.empty((Tmax, B, N), dtype=torch.float32, device=dev) if want_logits else None
         L = vrpx.lib()
         nbytes = int(L.vrpx_rollout_workspace_bytes(B, N))
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        ws = None
+        if self.score_tables and Tmax >= 3:
+            # table mode (include/vrpx.h, qk_w): per-episode glimpse score tables in a larger workspace
+            tbytes = int(L.vrpx_rollout_table_workspace_bytes(env._KIND, B, N))
+            try:
+                ws, nbytes = torch.empty((tbytes,), dtype=torch.uint8, device=dev), tbytes
+            except torch.cuda.OutOfMemoryError:
+                ws = None
+        if ws is None:
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         G = B if coupling is None else int(coupling)
         trace, saved = None, None
         if save_for_backward:
@@ -89,7 +99,7 @@ class GraphDecoder(nn.Module):
         env._host_cur = None
         out = {"cost": cost, "logp": logp, "steps": T, "tape": tape[:T], "coupling": G}
         if saved is not None:
-            saved["qg"] = ws[4096:].view(torch.float32).view(B, 1024)  # Q~g incl. the `first` fold (kRolloutSmall = 4096)
+            saved["qg"] = ws[4096:4096 + B * 4096].view(torch.float32).view(B, 1024)  # Q~g incl. the `first` fold (kRolloutSmall = 4096)
             saved["ws"] = ws
             out["saved"] = saved
         if logits is not None:

@@ -40,7 +40,14 @@ struct RolloutParams {
   unsigned* bar;      // grid barrier counter
   int* notdone;       // [Tmax + 1]
   long long* prof;    // optional [8] cycle counters per phase (debug, vrpx_debug_rollout_profile)
+  // table mode (score_table.cu): per-episode glimpse score tables, all NULL in the classic mode
+  const float* s1;    // [B][N][8][N]  (A_l h[b,l])_head · h[b,n], built before the launch
+  float* s0;          // [B][8][N]     Q~g[b]_head · h[b,n], built at step 1 (after the `first` fold)
+  float* sl;          // [B][8][N]     IRP: a_load_head · h[b,n]
 };
+
+int64_t score_table_slice(int64_t B);
+int build_score_table(const float* h, const float* qk_w, int64_t B, int N, float* qk_buf, float* s1, cudaStream_t stream);
 
 // Rollout tile: RMT x 16 instances.  With 16 instances per tile the working set that has to survive in L2 between the
 // glimpse passes and the pointer-logit pass (all CTAs x tile x 25.6 KB) halves to 60 MB.
@@ -116,16 +123,19 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       const int64_t base = tile * RTM;
       const int cnt = (int)((B - base < RTM) ? (B - base) : RTM);
       if (tid == 0) s_anyleft = 0;
+      // table mode: from step 2 on the glimpse scores come from the per-episode tables (no GEMM-A, no score pass)
+      const bool tbl_step = p.s1 != nullptr && t >= 2;
       // ---------------- P0: gather last-node embeddings, vehicle load; pull this tile's Q~g rows towards L2
-      for (int i = tid; i < cnt * 32; i += NT)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.qg + base * QW) + (size_t)i * 128));
+      if (!tbl_step)
+        for (int i = tid; i < cnt * 32; i += NT)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.qg + base * QW) + (size_t)i * 128));
       for (int m = warp; m < RTM; m += NT / 32) {
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < cnt && t > 0) {
+        if (m < cnt && t > 0 && !tbl_step) {
           int last = p.env.cur[base + m];
           xv = __ldg(reinterpret_cast<const float4*>(h + ((base + m) * N + last) * E) + lane);
         }
-        *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = xv;
+        if (!tbl_step) *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = xv;
         const float lf = (m < cnt) ? (float)p.env.load[base + m] : 0.f;
         if (lane == 0) s_loadf[m] = lf;
         if (m < cnt && p.mask_hist && lane < 4)
@@ -134,8 +144,71 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       }
       __syncthreads();
       VRPX_PROF(0)
+      // ---- glimpse score pass on the tensor pipe: S[node][head] = H_b[node][:] · q[head][:]  (m16n8k8, M = 16 nodes,
+      // N = 8 heads), q = 8 x 128 floats in shared memory.  Fragment coordinates g = lane >> 2, tq = lane & 3.  The K
+      // (embedding) axis is permuted so that every thread streams whole float4 chunks: chunk c (0..7) of thread tq
+      // covers dims 16c + 4tq + {0,1,2,3}; k-step 2c + u uses mma k-index tq <-> dim 16c+4tq+2u and k-index tq+4 <->
+      // dim 16c+4tq+2u+1, for A (node rows) and B (q) alike.  store(n, which, v): node n, head 2tq + which.
+      auto glimpse_scores = [&](const float* q, const float4* hrow, auto&& store) {
+        const int g = lane >> 2, tq = lane & 3;
+        float4 qv[8];   // q[head g][dims of this thread]
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qv[c] = *reinterpret_cast<const float4*>(q + g * E + 16 * c + 4 * tq);
+        __syncwarp();
+        for (int n0 = 0; n0 < N; n0 += 16) {
+          const int na = n0 + g, nbb = n0 + g + 8;
+          // six independent accumulator chains (3 split terms x even/odd k-step): a single chain would serialise the
+          // 96 mma of a node tile on the tensor-pipe latency
+          float acc6[2][3][4];
+#pragma unroll
+          for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+            for (int b_ = 0; b_ < 3; ++b_)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc6[a_][b_][i] = 0.f;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const int c = half * 4 + cc;
+              va[cc] = (na < N) ? __ldg(hrow + na * (E / 4) + 4 * c + tq) : make_float4(0.f, 0.f, 0.f, 0.f);
+              vb[cc] = (nbb < N) ? __ldg(hrow + nbb * (E / 4) + 4 * c + tq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const int c = half * 4 + cc;
+              const float ae[4] = {va[cc].x, va[cc].y, va[cc].z, va[cc].w};
+              const float be[4] = {vb[cc].x, vb[cc].y, vb[cc].z, vb[cc].w};
+              const float qe[4] = {qv[c].x, qv[c].y, qv[c].z, qv[c].w};
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+                split_tf32(ae[2 * u], ah[0], al[0]);       // (row g,   k = tq)
+                split_tf32(be[2 * u], ah[1], al[1]);       // (row g+8, k = tq)
+                split_tf32(ae[2 * u + 1], ah[2], al[2]);   // (row g,   k = tq+4)
+                split_tf32(be[2 * u + 1], ah[3], al[3]);   // (row g+8, k = tq+4)
+                split_tf32(qe[2 * u], bh0, bl0);           // (k = tq,   n = g)
+                split_tf32(qe[2 * u + 1], bh1, bl1);       // (k = tq+4, n = g)
+                mma_tf32_16x8x8(acc6[u][0], al, bh0, bh1);
+                mma_tf32_16x8x8(acc6[u][1], ah, bl0, bl1);
+                mma_tf32_16x8x8(acc6[u][2], ah, bh0, bh1);
+              }
+            }
+          }
+          float acc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            acc[i] = ((acc6[0][0][i] + acc6[1][0][i]) + (acc6[0][1][i] + acc6[1][1][i])) + (acc6[0][2][i] + acc6[1][2][i]);
+          // C fragment: acc[0], acc[1] = node na, heads 2tq, 2tq+1;  acc[2], acc[3] = node nbb
+          if (na < N) { store(na, 0, acc[0]); store(na, 1, acc[1]); }
+          if (nbb < N) { store(nbb, 0, acc[2]); store(nbb, 1, acc[3]); }
+        }
+      };
       // ---------------- P1: q~
-      if (t == 0) {
+      if (tbl_step) {
+        // nothing: scores are gathered from S1/S0 in P2
+      } else if (t == 0) {
         for (int o = tid; o < cnt * QW; o += NT) {
           int m = o >> 10, c = o & (QW - 1);
           float y = p.qg[(base + m) * QW + c] + p.w.a_q0[c];
@@ -152,6 +225,30 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
               [&](int m, int c, float v0, float v1) {
                 if (m < cnt) *reinterpret_cast<float2*>(p.qg + (base + m) * QW + c) = make_float2(v0, v1);
               });
+        }
+        if (t == 1 && p.s1) {
+          // table mode: Q~g is final now -> S0[b][head][n] = Q~g[b]_head · h[b,n]  (IRP: SL from a_load as well)
+          __syncthreads();
+          for (int m = warp; m < cnt; m += NT / 32) {
+            const int64_t b = base + m;
+            float* slot = QC + m * QC_LD;
+            const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
+            const int tq = lane & 3;
+            for (int i = lane; i < QW / 4; i += 32)
+              *reinterpret_cast<float4*>(slot + 4 * i) = __ldcg(reinterpret_cast<const float4*>(p.qg + b * QW) + i);
+            __syncwarp();
+            float* s0 = p.s0 + (size_t)b * NH * N;
+            glimpse_scores(slot, hrow, [&](int n, int which, float v) { s0[(2 * tq + which) * N + n] = v; });
+            if (kind == VRPX_IRP) {
+              __syncwarp();
+              for (int i = lane; i < QW / 4; i += 32)
+                *reinterpret_cast<float4*>(slot + 4 * i) = __ldg(reinterpret_cast<const float4*>(p.w.a_load) + i);
+              __syncwarp();
+              float* sl = p.sl + (size_t)b * NH * N;
+              glimpse_scores(slot, hrow, [&](int n, int which, float v) { sl[(2 * tq + which) * N + n] = v; });
+            }
+          }
+          __syncthreads();
         }
         tile_gemm_wide_mma<RMT>(                                          // q~ = Q~g (+ load · a_load) + A_l · h[last]
             Xs, p.w.al_t, Wb,
@@ -174,92 +271,63 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       for (int m = warp; m < cnt; m += NT / 32) {
         const int64_t b = base + m;
         float* slot = QC + m * QC_LD;
-        // ---- pass 1 on the tensor pipe: S[node][head] = H_b[node][:] · q~[head][:]  (m16n8k8, M = 16 nodes, N = 8 heads)
-        // Fragment coordinates g = lane >> 2, t = lane & 3.  The K (embedding) axis is permuted so that every thread
-        // streams whole float4 chunks: chunk c (0..7) of thread t covers dims 16c + 4t + {0,1,2,3}; k-step 2c + u uses
-        // mma k-index t <-> dim 16c+4t+2u and k-index t+4 <-> dim 16c+4t+2u+1, for A (node rows) and B (q~) alike.
         const int g = lane >> 2, t = lane & 3;
-        float4 qv[8];   // q~[head g][dims of this thread]
-#pragma unroll
-        for (int c = 0; c < 8; ++c) qv[c] = *reinterpret_cast<const float4*>(slot + g * E + 16 * c + 4 * t);
-        __syncwarp();
-        // masks of the instances whose rows the reference adds to heads 2t and 2t+1 (mask.repeat(H,1), graph_decoder.py:93)
-        uint32_t nb0[4], nb1[4];
-        {
-          const uint32_t* m0 = p.env.mask + quirk_row(b, 2 * t, p.G) * 4;
-          const uint32_t* m1 = p.env.mask + quirk_row(b, 2 * t + 1, p.G) * 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { nb0[i] = __ldcg(m0 + i); nb1[i] = __ldcg(m1 + i); }
-        }
         const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
-        for (int n0 = 0; n0 < N; n0 += 16) {
-          const int na = n0 + g, nbb = n0 + g + 8;
-          // six independent accumulator chains (3 split terms x even/odd k-step): a single chain would serialise the
-          // 96 mma of a node tile on the tensor-pipe latency
-          float acc6[2][3][4];
-#pragma unroll
-          for (int a_ = 0; a_ < 2; ++a_)
-#pragma unroll
-            for (int b_ = 0; b_ < 3; ++b_)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) acc6[a_][b_][i] = 0.f;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 va[4], vb[4];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const int c = half * 4 + cc;
-              va[cc] = (na < N) ? __ldg(hrow + na * (E / 4) + 4 * c + t) : make_float4(0.f, 0.f, 0.f, 0.f);
-              vb[cc] = (nbb < N) ? __ldg(hrow + nbb * (E / 4) + 4 * c + t) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const int c = half * 4 + cc;
-              const float ae[4] = {va[cc].x, va[cc].y, va[cc].z, va[cc].w};
-              const float be[4] = {vb[cc].x, vb[cc].y, vb[cc].z, vb[cc].w};
-              const float qe[4] = {qv[c].x, qv[c].y, qv[c].z, qv[c].w};
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
-                split_tf32(ae[2 * u], ah[0], al[0]);       // (row g,   k = t)
-                split_tf32(be[2 * u], ah[1], al[1]);       // (row g+8, k = t)
-                split_tf32(ae[2 * u + 1], ah[2], al[2]);   // (row g,   k = t+4)
-                split_tf32(be[2 * u + 1], ah[3], al[3]);   // (row g+8, k = t+4)
-                split_tf32(qe[2 * u], bh0, bl0);           // (k = t,   n = g)
-                split_tf32(qe[2 * u + 1], bh1, bl1);       // (k = t+4, n = g)
-                mma_tf32_16x8x8(acc6[u][0], al, bh0, bh1);
-                mma_tf32_16x8x8(acc6[u][1], ah, bl0, bl1);
-                mma_tf32_16x8x8(acc6[u][2], ah, bh0, bh1);
-              }
-            }
-          }
-          float acc[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            acc[i] = ((acc6[0][0][i] + acc6[1][0][i]) + (acc6[0][1][i] + acc6[1][1][i])) + (acc6[0][2][i] + acc6[1][2][i]);
-          // C fragment: acc[0], acc[1] = node na, heads 2t, 2t+1;  acc[2], acc[3] = node nbb
-          if (na < N) {
-            slot[(2 * t) * E + na] = acc[0] + (float)((nb0[na >> 5] >> (na & 31)) & 1u);
-            slot[(2 * t + 1) * E + na] = acc[1] + (float)((nb1[na >> 5] >> (na & 31)) & 1u);
-          }
-          if (nbb < N) {
-            slot[(2 * t) * E + nbb] = acc[2] + (float)((nb0[nbb >> 5] >> (nbb & 31)) & 1u);
-            slot[(2 * t + 1) * E + nbb] = acc[3] + (float)((nb1[nbb >> 5] >> (nbb & 31)) & 1u);
-          }
-        }
-        __syncwarp();
-        VRPX_PROF(6)
-        // softmax per head over nodes (lane = node, 4 strides cover N <= 128)
         float pr[NH][4];
+        if (!tbl_step) {
+          // ---- pass 1: scores = q~_h · h_n + scrambled additive mask
+          // masks of the instances whose rows the reference adds to heads 2t and 2t+1 (mask.repeat(H,1), graph_decoder.py:93)
+          uint32_t nb0[4], nb1[4];
+          {
+            const uint32_t* m0 = p.env.mask + quirk_row(b, 2 * t, p.G) * 4;
+            const uint32_t* m1 = p.env.mask + quirk_row(b, 2 * t + 1, p.G) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { nb0[i] = __ldcg(m0 + i); nb1[i] = __ldcg(m1 + i); }
+          }
+          glimpse_scores(slot, hrow, [&](int n, int which, float v) {
+            const uint32_t wsel = which ? nb1[n >> 5] : nb0[n >> 5];
+            slot[(2 * t + which) * E + n] = v + (float)((wsel >> (n & 31)) & 1u);
+          });
+          __syncwarp();
+          VRPX_PROF(6)
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = lane + 32 * i;
+              pr[hh][i] = (n < N) ? slot[hh * E + n] : -INFINITY;
+            }
+        } else {
+          // ---- table mode: scores = S1[b][last] + S0[b] (+ load · SL[b]) + scrambled additive mask
+          const int last = __ldcg(p.env.cur + b);
+          const float* r1 = p.s1 + (((size_t)b * N + last) * NH) * N;
+          const float* r0 = p.s0 + (size_t)b * NH * N;
+          const float* rl = p.sl + (size_t)b * NH * N;
+          const float lf = s_loadf[m];
+          // lane j holds mask word (j & 3) of the instance whose mask the reference adds to head j >> 2
+          const uint32_t mword = __ldcg(p.env.mask + quirk_row(b, lane >> 2, p.G) * 4 + (lane & 3));
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = lane + 32 * i;
+              const uint32_t wsel = __shfl_sync(0xffffffffu, mword, hh * 4 + i);
+              float v = -INFINITY;
+              if (n < N) {
+                v = __ldg(r1 + hh * N + n) + __ldcg(r0 + hh * N + n);
+                if (kind == VRPX_IRP) v = fmaf(lf, __ldcg(rl + hh * N + n), v);
+                v += (float)((wsel >> lane) & 1u);
+              }
+              pr[hh][i] = v;
+            }
+          VRPX_PROF(6)
+        }
+        // softmax per head over nodes (lane = node, 4 strides cover N <= 128)
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) {
           float mx = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int n = lane + 32 * i;
-            pr[hh][i] = (n < N) ? slot[hh * E + n] : -INFINITY;
-            mx = fmaxf(mx, pr[hh][i]);
-          }
+          for (int i = 0; i < 4; ++i) mx = fmaxf(mx, pr[hh][i]);
           mx = warp_max(mx);
           float sum = 0.f;
 #pragma unroll
@@ -507,6 +575,26 @@ int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N) {
   return kRolloutSmall + B * (int64_t)QW * (int64_t)sizeof(float);
 }
 
+// table-mode workspace: header | Q~g | S0 | SL (IRP) | S1 | QK slice, every segment 256-byte aligned
+namespace {
+struct TableLayout {
+  int64_t s0, sl, s1, qk, total;
+};
+inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+TableLayout table_layout(int kind, int64_t B, int N) {
+  TableLayout L;
+  const int64_t f = (int64_t)sizeof(float);
+  L.s0 = align256(kRolloutSmall + B * QW * f);
+  L.sl = align256(L.s0 + B * NH * N * f);
+  L.s1 = (kind == VRPX_IRP) ? align256(L.sl + B * NH * N * f) : L.sl;
+  L.qk = align256(L.s1 + B * N * NH * N * f);
+  L.total = align256(L.qk + score_table_slice(B) * N * 768 * f);
+  return L;
+}
+}  // namespace
+
+int64_t vrpx_rollout_table_workspace_bytes(int32_t kind, int64_t B, int32_t N) { return table_layout(kind, B, N).total; }
+
 int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float* h, int32_t mode,
                  int64_t coupling, uint64_t seed, uint64_t offset, uint8_t* tape, int32_t t_begin, int32_t Tmax,
                  float* logp, float* cost, int32_t* steps, float* logits, const vrpx_rollout_trace* trace,
@@ -547,6 +635,21 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   p.bar = reinterpret_cast<unsigned*>(ws);
   p.notdone = reinterpret_cast<int*>(ws) + 8;
   p.qg = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kRolloutSmall);
+  p.s1 = nullptr;
+  p.s0 = p.sl = nullptr;
+  // table mode: whole-episode call with the large workspace and the rank-48 factors
+  if (w->qk_w && t_begin == 0 && Tmax >= 3) {
+    const TableLayout L = table_layout(env->kind, env->B, env->N);
+    if (ws_bytes >= L.total && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+      char* base = reinterpret_cast<char*>(ws);
+      float* s1 = reinterpret_cast<float*>(base + L.s1);
+      int rc = build_score_table(h, w->qk_w, env->B, env->N, reinterpret_cast<float*>(base + L.qk), s1, stream);
+      if (rc) return rc;
+      p.s1 = s1;
+      p.s0 = reinterpret_cast<float*>(base + L.s0);
+      p.sl = reinterpret_cast<float*>(base + L.sl);
+    }
+  }
   VRPX_CHECK_ARG((int64_t)(Tmax + 1 + 8) * 4 <= kRolloutSmall, "Tmax too large for workspace header");
 
   VRPX_CUDA(cudaMemsetAsync(ws, 0, kRolloutSmall, stream));

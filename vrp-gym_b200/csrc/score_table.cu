@@ -1,0 +1,137 @@
+// score_table.cu — per-episode glimpse score table for the fused rollout (table mode of vrpx_rollout).
+//
+// The decoder's glimpse scores at step t >= 1 are  s[b,head,n] = q~[b,head] · h[b,n]  with
+// q~ = A_l · h[b,last] + Q~g[b]  (agents/graph_decoder.py:75-94 after the folding of vrpx/packing.py).  The part that
+// depends on the step, (A_l h[b,l])_head · h[b,n], takes only N different values of l per instance, and A_l has rank 48
+// per head (A_l,head = W_k,head^T · W_l,head / sqrt(48), the reference's own query/key projections).  So once per
+// episode:
+//     QK = h · qk_w^T                      (B·N) x 768 on tcgen05 (gemm_tc): q'[b,l] | k'[b,n], 8 heads x 48
+//     S1[b][l][head][n] = q'[b,l,head] · k'[b,n,head]        this kernel, mma.sync TF32 3-term split
+// and the decode steps read the 8·N scores of row (b, last) instead of running the 128 -> 1024 tile GEMM and the
+// 8·N·128 score pass every step.  Algorithmic cost: the table holds B·N·8·N floats (5.2 GB at TSP-50, B = 65536).
+#include "gemm.cuh"
+#include "tile_gemm.cuh"
+
+namespace vrpx {
+
+constexpr int DQK = 48;            // decoder head dim (384 / 8)
+constexpr int QKW = 2 * NH * DQK;  // 768 columns of QK
+
+// One CTA per instance, one warp per head.  The warp stages k'[b, :, head] (N x 48, unpadded: LDS.128 of the B
+// fragments is conflict free at a 48-float pitch) in shared memory, streams q' rows from global memory as A fragments
+// and writes S1 rows.  The K axis (48) is permuted so that every thread loads whole float4 chunks: chunk c (0..2) of
+// thread t covers dims 16c + 4t + {0,1,2,3}; k-step 2c + u uses mma k-index t <-> dim 16c+4t+2u and t+4 <-> 16c+4t+2u+1.
+template <int NT8>
+__global__ void __launch_bounds__(256) k_score_table(const float* __restrict__ qk, float* __restrict__ s1, int N) {
+  extern __shared__ __align__(16) float ks_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t b = blockIdx.x;
+  float* Ks = ks_all + warp * (NT8 * 8 * DQK);
+  const float* qkb = qk + b * N * QKW;
+  for (int idx = lane; idx < NT8 * 8 * (DQK / 4); idx += 32) {
+    const int n = idx / (DQK / 4), c4 = idx % (DQK / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) v = __ldg(reinterpret_cast<const float4*>(qkb + (size_t)n * QKW + NH * DQK + warp * DQK) + c4);
+    *reinterpret_cast<float4*>(Ks + n * DQK + c4 * 4) = v;
+  }
+  __syncwarp();
+  const bool vec_ok = (N & 1) == 0;
+  for (int l0 = 0; l0 < N; l0 += 16) {
+    const int la = l0 + g, lb = l0 + g + 8;
+    float acc[NT8][4];
+#pragma unroll
+    for (int j = 0; j < NT8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    float4 qa[3], qb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      qa[c] = (la < N) ? __ldg(reinterpret_cast<const float4*>(qkb + (size_t)la * QKW + warp * DQK + 16 * c) + t)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      qb[c] = (lb < N) ? __ldg(reinterpret_cast<const float4*>(qkb + (size_t)lb * QKW + warp * DQK + 16 * c) + t)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float ae[4] = {qa[c].x, qa[c].y, qa[c].z, qa[c].w};
+      const float be[4] = {qb[c].x, qb[c].y, qb[c].z, qb[c].w};
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        split_tf32(ae[2 * u], ah[u][0], al[u][0]);       // (row g,   k = t)
+        split_tf32(be[2 * u], ah[u][1], al[u][1]);       // (row g+8, k = t)
+        split_tf32(ae[2 * u + 1], ah[u][2], al[u][2]);   // (row g,   k = t+4)
+        split_tf32(be[2 * u + 1], ah[u][3], al[u][3]);   // (row g+8, k = t+4)
+      }
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) {
+        const float4 kv = *reinterpret_cast<const float4*>(Ks + (8 * j + g) * DQK + 16 * c + 4 * t);
+        const float ke[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32(ke[2 * u], bh0, bl0);       // (k = t,   n = g)
+          split_tf32(ke[2 * u + 1], bh1, bl1);   // (k = t+4, n = g)
+          mma_tf32_16x8x8(acc[j], al[u], bh0, bh1);
+          mma_tf32_16x8x8(acc[j], ah[u], bl0, bl1);
+          mma_tf32_16x8x8(acc[j], ah[u], bh0, bh1);
+        }
+      }
+    }
+    // C fragment: acc[j][0..1] = (l = la, n = 8j + 2t, +1), acc[j][2..3] = (l = lb, ...)
+    float* ra = s1 + (((size_t)b * N + la) * NH + warp) * N;
+    float* rb = s1 + (((size_t)b * N + lb) * NH + warp) * N;
+#pragma unroll
+    for (int j = 0; j < NT8; ++j) {
+      const int n = 8 * j + 2 * t;
+      if (vec_ok) {
+        if (n < N) {
+          if (la < N) *reinterpret_cast<float2*>(ra + n) = make_float2(acc[j][0], acc[j][1]);
+          if (lb < N) *reinterpret_cast<float2*>(rb + n) = make_float2(acc[j][2], acc[j][3]);
+        }
+      } else {
+        if (la < N) {
+          if (n < N) ra[n] = acc[j][0];
+          if (n + 1 < N) ra[n + 1] = acc[j][1];
+        }
+        if (lb < N) {
+          if (n < N) rb[n] = acc[j][2];
+          if (n + 1 < N) rb[n + 1] = acc[j][3];
+        }
+      }
+    }
+  }
+}
+
+template <int NT8>
+static int launch_score_table(const float* qk, float* s1, int64_t nb, int N, cudaStream_t stream) {
+  const int smem = NH * NT8 * 8 * DQK * (int)sizeof(float);
+  VRPX_CUDA(cudaFuncSetAttribute(k_score_table<NT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_score_table<NT8><<<(unsigned)nb, 256, smem, stream>>>(qk, s1, N);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+int64_t score_table_slice(int64_t B) { return B < 16384 ? B : 16384; }
+
+// S1[B][N][8][N] from h [B][N][128] and qk_w [768][128]; qk_buf holds score_table_slice(B)·N·768 floats.
+int build_score_table(const float* h, const float* qk_w, int64_t B, int N, float* qk_buf, float* s1,
+                      cudaStream_t stream) {
+  const int64_t slice = score_table_slice(B);
+  const int nt = (N + 7) / 8;
+  for (int64_t b0 = 0; b0 < B; b0 += slice) {
+    const int64_t nb = (B - b0 < slice) ? (B - b0) : slice;
+    GemmArgs ga{h + b0 * N * E, nb * N, E, qk_w, QKW, nullptr, 0, nullptr, nullptr, nullptr, qk_buf};
+    int rc = gemm_tc(ga, stream);
+    if (rc) return rc;
+    float* dst = s1 + (size_t)b0 * N * NH * N;
+    if (nt <= 3) rc = launch_score_table<3>(qk_buf, dst, nb, N, stream);
+    else if (nt <= 7) rc = launch_score_table<7>(qk_buf, dst, nb, N, stream);
+    else if (nt <= 13) rc = launch_score_table<13>(qk_buf, dst, nb, N, stream);
+    else rc = launch_score_table<16>(qk_buf, dst, nb, N, stream);
+    if (rc) return rc;
+  }
+  return VRPX_OK;
+}
+
+}  // namespace vrpx

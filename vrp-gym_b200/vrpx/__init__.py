@@ -52,7 +52,7 @@ class RolloutTrace(C.Structure):
 
 
 class DecoderWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("ag_t", "af_t", "al_t", "a_c", "a_q0", "a_load", "m_t", "m_c")]
+    _fields_ = [(n, C.c_void_p) for n in ("ag_t", "af_t", "al_t", "a_c", "a_q0", "a_load", "m_t", "m_c", "qk_w")]
 
 
 class DecoderBwdWeights(C.Structure):
@@ -124,10 +124,12 @@ def lib():
     L.vrpx_episode_scatter.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.vrpx_rollout_workspace_bytes.argtypes = [i64, i32]
     L.vrpx_rollout_workspace_bytes.restype = i64
+    L.vrpx_rollout_table_workspace_bytes.argtypes = [i32, i64, i32]
+    L.vrpx_rollout_table_workspace_bytes.restype = i64
     L.vrpx_rollout.argtypes = [C.POINTER(EnvView), C.POINTER(DecoderWeights), vp, i32, i64, u64, u64, vp, i32, i32,
                                vp, vp, vp, vp, C.POINTER(RolloutTrace), vp, i64, vp]
     L.vrpx_debug_gemm.argtypes = [vp, i64, i32, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp]
-    if L.vrpx_abi_version() != 1:
+    if L.vrpx_abi_version() != 2:
         raise VrpxError("libvrpx.so ABI version mismatch")
     _lib = L
     return L

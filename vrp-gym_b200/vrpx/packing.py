@@ -66,6 +66,8 @@ def fold_decoder(dec, irp: bool, dtype=torch.float64):
             "a_load": None,
         }
     out["a_c"] = kfold(bq[:, None])[:, 0].contiguous()
+    # rank-48 factors of al_t per head (score-table mode of vrpx_rollout): q' = W_l h / sqrt(48), k' = W_k h
+    out["qk_w"] = torch.cat([Wl / math.sqrt(DH), Wk], dim=0).contiguous()   # (768, 128)
     F = (Wkp.T @ Wao @ Wo) / math.sqrt(E)              # (128, 384)
     # m_t[h*128 + d, e] = sum_j F[e, 48h+j] * Wv[48h+j, d]
     out["m_t"] = torch.einsum("ehj,hjd->hde", F.view(E, H, DH), Wv.view(H, DH, E)).reshape(H * E, E).contiguous()
