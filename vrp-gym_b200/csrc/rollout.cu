@@ -44,6 +44,7 @@ struct RolloutParams {
   const float* s1;    // [B][N][8][N]  (A_l h[b,l])_head · h[b,n], built before the launch
   float* s0;          // [B][8][N]     Q~g[b]_head · h[b,n], built at step 1 (after the `first` fold)
   float* sl;          // [B][8][N]     IRP: a_load_head · h[b,n]
+  int tb_segs;        // table rows staged in shared memory per instance: 0 none, 1 = S1, 2 = S1 + S0, 3 = S1 + S0 + SL
 };
 
 int64_t score_table_slice(int64_t B);
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
   float* Xs = reinterpret_cast<float*>(smem_raw);
   float* QC = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA);
   float* Wb = reinterpret_cast<float*>(smem_raw + SMEM_X_MMA + SMEM_QC_MMA);
+  float* TB = reinterpret_cast<float*>(smem_raw + SMEM_TOTAL);   // [RTM][tb_segs][8 N] staged table rows (table mode)
   __shared__ float s_loadf[RTM], s_lp[RTM];
   __shared__ int s_anyleft, s_act[RTM];
 
@@ -114,6 +116,33 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         });
     __syncthreads();
   }
+
+  // Table mode: the rows S1[b][last], S0[b] (, SL[b]) the NEXT tile will need are copied to shared memory with cp.async
+  // while the current tile runs its pointer-logit phase, so the dependent chain cur -> table row -> softmax does not
+  // sit exposed at the head of every tile.  One warp per instance, issued and consumed by the same warp.
+  const int tb_row = NH * N;                    // floats per staged segment
+  const int tb_stride = p.tb_segs * tb_row;     // floats per instance
+  bool staged = false;                          // TB holds the rows of the tile about to be processed
+  auto stage_tables = [&](int64_t ntile) {
+    const int64_t nbase = ntile * RTM;
+    const int ncnt = (int)((B - nbase < RTM) ? (B - nbase) : RTM);
+    for (int m = warp; m < ncnt; m += NT / 32) {
+      const int64_t b = nbase + m;
+      const int last = __ldcg(p.env.cur + b);
+      float* dst = TB + m * tb_stride;
+      const float* src1 = p.s1 + (((size_t)b * N + last) * NH) * N;
+      for (int i = lane; i < tb_row / 4; i += 32) cp_async16(dst + 4 * i, src1 + 4 * i);
+      if (p.tb_segs >= 2) {
+        const float* src0 = p.s0 + (size_t)b * tb_row;
+        for (int i = lane; i < tb_row / 4; i += 32) cp_async16(dst + tb_row + 4 * i, src0 + 4 * i);
+      }
+      if (p.tb_segs >= 3) {
+        const float* srcl = p.sl + (size_t)b * tb_row;
+        for (int i = lane; i < tb_row / 4; i += 32) cp_async16(dst + 2 * tb_row + 4 * i, srcl + 4 * i);
+      }
+    }
+    cp_async_commit();
+  };
 
   int t = p.t0;
   for (; t < p.t0 + p.Tmax; ++t) {
@@ -299,10 +328,19 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
             }
         } else {
           // ---- table mode: scores = S1[b][last] + S0[b] (+ load · SL[b]) + scrambled additive mask
-          const int last = __ldcg(p.env.cur + b);
-          const float* r1 = p.s1 + (((size_t)b * N + last) * NH) * N;
+          const float* r1;
           const float* r0 = p.s0 + (size_t)b * NH * N;
           const float* rl = p.sl + (size_t)b * NH * N;
+          if (staged) {
+            cp_async_wait<0>();
+            __syncwarp();
+            r1 = TB + m * tb_stride;
+            if (p.tb_segs >= 2) r0 = r1 + tb_row;
+            if (p.tb_segs >= 3) rl = r1 + 2 * tb_row;
+          } else {
+            const int last = __ldcg(p.env.cur + b);
+            r1 = p.s1 + (((size_t)b * N + last) * NH) * N;
+          }
           const float lf = s_loadf[m];
           // lane j holds mask word (j & 3) of the instance whose mask the reference adds to head j >> 2
           const uint32_t mword = __ldcg(p.env.mask + quirk_row(b, lane >> 2, p.G) * 4 + (lane & 3));
@@ -314,8 +352,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
               const uint32_t wsel = __shfl_sync(0xffffffffu, mword, hh * 4 + i);
               float v = -INFINITY;
               if (n < N) {
-                v = __ldg(r1 + hh * N + n) + __ldcg(r0 + hh * N + n);
-                if (kind == VRPX_IRP) v = fmaf(lf, __ldcg(rl + hh * N + n), v);
+                v = r1[hh * N + n] + r0[hh * N + n];   // generic loads: shared (staged) or global (L2-coherent data)
+                if (kind == VRPX_IRP) v = fmaf(lf, rl[hh * N + n], v);
                 v += (float)((wsel >> lane) & 1u);
               }
               pr[hh][i] = v;
@@ -409,6 +447,18 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
       tile_gemm_tall_mma<RMT>(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
 
+      // table mode: start copying the next tile's table rows (its `cur` is final: written one step ago, or — when the
+      // next tile is this CTA's first tile of the NEXT step — earlier in this step)
+      staged = false;
+      if (p.s1 && p.tb_segs > 0) {
+        int64_t ntile = tile + gridDim.x;
+        int tn = t;
+        if (ntile >= ntiles) { ntile = blockIdx.x; tn = t + 1; }
+        if (tn >= 2 && ntile != tile) {
+          stage_tables(ntile);
+          staged = true;
+        }
+      }
       VRPX_PROF(3)
       // ---------------- P4: logits, action, environment transition
       bool unfinished = false;
@@ -553,6 +603,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
     VRPX_PROF(5)
     if (ld_acquire_i(p.notdone + trel) == 0) { ++t; break; }
   }
+  cp_async_wait<0>();
   if (p.prof && tid == 0)
     for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(p.prof) + i, (unsigned long long)prof_acc[i]);
   if (blockIdx.x == 0 && tid == 0) *p.steps = t;
@@ -650,14 +701,24 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
       p.sl = reinterpret_cast<float*>(base + L.sl);
     }
   }
+  // shared-memory staging of the table rows: as many segments as fit beside the GEMM buffers
+  p.tb_segs = 0;
+  size_t smem_total = SMEM_TOTAL;
+  if (p.s1) {
+    const size_t avail = 227 * 1024 - SMEM_TOTAL - 1024;   // 1 KiB for the static __shared__ arrays
+    const size_t seg = (size_t)RTM * NH * env->N * sizeof(float);
+    const int want = (env->kind == VRPX_IRP) ? 3 : 2;
+    p.tb_segs = (int)((avail / seg < (size_t)want) ? avail / seg : (size_t)want);
+    smem_total += p.tb_segs * seg;
+  }
   VRPX_CHECK_ARG((int64_t)(Tmax + 1 + 8) * 4 <= kRolloutSmall, "Tmax too large for workspace header");
 
   VRPX_CUDA(cudaMemsetAsync(ws, 0, kRolloutSmall, stream));
-  VRPX_CUDA(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+  VRPX_CUDA(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
   int64_t ntiles = (env->B + RTM - 1) / RTM;
   int grid = (int)((ntiles < (int64_t)num_sms()) ? ntiles : (int64_t)num_sms());
   void* args[] = {(void*)&p};
-  VRPX_CUDA(cudaLaunchCooperativeKernel((void*)k_rollout, dim3(grid), dim3(NT), args, SMEM_TOTAL, stream));
+  VRPX_CUDA(cudaLaunchCooperativeKernel((void*)k_rollout, dim3(grid), dim3(NT), args, smem_total, stream));
   count_launch();
   return VRPX_OK;
 }
