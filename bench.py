@@ -271,9 +271,12 @@ def main():
     w0 = time.perf_counter()
     e0.record()
     total_inst_steps = 0
+    kernel_ms = []
+    vrpx.lib().vrpx_debug_rollout_timing(1)  # CUDA events around the persistent kernel alone, on its launch stream
     for i in range(a.steps):
         out = one_step(per_step_events[i])
         total_inst_steps += out["steps"] * B  # includes the .item() sync on the step count
+        kernel_ms.append(float(vrpx.lib().vrpx_debug_rollout_kernel_ms()))  # the step is already synchronised
     e1.record()
     barrier()
     w1 = time.perf_counter()
@@ -282,6 +285,8 @@ def main():
     enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in per_step_events]))
     roll_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in per_step_events]))
     mean_cost = float(out["cost"].mean().item())
+    vrpx.lib().vrpx_debug_rollout_timing(0)
+    kern_ms = float(np.mean(kernel_ms))
 
     # ---- e2e: public API with host buffers (pinned H2D of the instances, D2H of the costs inside the timed region)
     s = env.sampler
@@ -311,12 +316,12 @@ def main():
     d2h = int(B * 4)
 
     # ---- max over ranks
-    t = torch.tensor([elapsed_ms, e2e_ms, roll_ms, enc_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([elapsed_ms, e2e_ms, roll_ms, enc_ms, kern_ms], device=dev, dtype=torch.float64)
     tot = torch.tensor([float(total_inst_steps), float(e2e_inst_steps)], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, roll_ms, enc_ms = [float(x) for x in t.tolist()]
+    elapsed_ms, e2e_ms, roll_ms, enc_ms, kern_ms = [float(x) for x in t.tolist()]
     total_inst_steps, e2e_inst_steps = [float(x) for x in tot.tolist()]
 
     if rank == 0:
@@ -332,7 +337,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", f"rollout_traffic_{a.kind}{N}_b{B}.json")
         if os.path.exists(tpath):
             traffic = float(json.load(open(tpath))["dram_bytes_per_launch"])
-        achieved = alg_bytes / (roll_ms * 1e-3) / 1e9
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         value = total_inst_steps / (elapsed_ms * 1e-3)
         line = {
             "metric": "instance_steps_per_sec", "value": value, "unit": "instance-steps/s", "n_gpus": world,
@@ -346,14 +351,14 @@ def main():
                        "l2": "inputs larger than L2 (embeddings %.2f GB per GPU re-streamed every decode step)" % (B * N * 512 / 1e9)},
             "rollouts_per_sec": value / T,
             "mean_cost": mean_cost,
-            "breakdown_ms": {"encoder": enc_ms, "rollout_kernel": roll_ms},
+            "breakdown_ms": {"encoder": enc_ms, "score_tables": roll_ms - kern_ms, "rollout_kernel": kern_ms},
             "clocks": clk,
             "e2e": {"value": e2e_inst_steps / (e2e_ms * 1e-3), "unit": "instance-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": n_e2e},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_rollout (persistent decoder+env)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": roll_ms},
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms},
         }
         if not a.no_cpu_baseline:
             rate, sec, threads = cpu_rollout_rate(a.kind, N, a.cpu_batch, a.seed)

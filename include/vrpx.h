@@ -224,6 +224,16 @@ VRPX_API int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, co
                  float* logp, float* cost, int32_t* steps, float* logits, const vrpx_rollout_trace* trace,
                  void* ws, int64_t ws_bytes, void* stream);
 
+/* Measurement hooks (bench.py, tools/): not part of the reference surface.
+ *   vrpx_debug_rollout_profile  device buffer of 8 x int64 that accumulates per-phase cycles of thread 0 of every CTA
+ *                               of the rollout kernel (NULL disables)
+ *   vrpx_debug_rollout_timing   when enabled, vrpx_rollout brackets the persistent kernel launch (alone, without the
+ *                               score-table prologue kernels) with CUDA events on the launch stream
+ *   vrpx_debug_rollout_kernel_ms  waits for the last bracketed launch and returns its duration (-1 if none) */
+VRPX_API void vrpx_debug_rollout_profile(long long* dev_counters);
+VRPX_API void vrpx_debug_rollout_timing(int32_t enable);
+VRPX_API float vrpx_debug_rollout_kernel_ms(void);
+
 /* ---------------------------------------------------------------- REINFORCE backward (decoder part)
  * loss = mean_b(advantage_b * sum_t log p(a_{b,t}))  (agents/graph_tsp_agent.py:179-186).  The backward is
  * recompute-based: it replays every decode step from (h, tape, trace) and back-propagates wts[b] = dL/dlogp_b. */

@@ -24,7 +24,9 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14, names
     for n in names:
         assert hasattr(L, n), f"libvrpx.so does not export {n}"
-    assert L.vrpx_abi_version() == 2
+    assert L.vrpx_abi_version() == vrpx.ABI_VERSION
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'vrpx.h')).read()
+    assert f'#define VRPX_ABI_VERSION {vrpx.ABI_VERSION}' in header
     assert L.vrpx_launch_count() == 0
 
 

@@ -610,6 +610,9 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
 }
 
 static long long* g_rollout_prof = nullptr;
+static int g_time_kernel = 0;                        // vrpx_debug_rollout_timing
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static bool g_ev_valid = false;
 constexpr int64_t kRolloutSmall = 4096;  // barrier counter + notdone[<=513]
 
 }  // namespace vrpx
@@ -619,7 +622,19 @@ using namespace vrpx;
 extern "C" {
 
 /* Debug hook: device buffer of 8 x int64 that accumulates per-phase cycles of thread 0 of every CTA (NULL disables). */
-VRPX_API void vrpx_debug_rollout_profile(long long* dev_counters) { g_rollout_prof = dev_counters; }
+void vrpx_debug_rollout_profile(long long* dev_counters) { g_rollout_prof = dev_counters; }
+
+void vrpx_debug_rollout_timing(int32_t enable) {
+  g_time_kernel = enable;
+  g_ev_valid = false;
+}
+
+float vrpx_debug_rollout_kernel_ms(void) {
+  if (!g_ev_valid) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(g_ev1) != cudaSuccess || cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
 
 int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N) {
   (void)N;
@@ -718,8 +733,19 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   int64_t ntiles = (env->B + RTM - 1) / RTM;
   int grid = (int)((ntiles < (int64_t)num_sms()) ? ntiles : (int64_t)num_sms());
   void* args[] = {(void*)&p};
+  if (g_time_kernel) {
+    if (!g_ev0) {
+      VRPX_CUDA(cudaEventCreate(&g_ev0));
+      VRPX_CUDA(cudaEventCreate(&g_ev1));
+    }
+    VRPX_CUDA(cudaEventRecord(g_ev0, stream));
+  }
   VRPX_CUDA(cudaLaunchCooperativeKernel((void*)k_rollout, dim3(grid), dim3(NT), args, smem_total, stream));
   count_launch();
+  if (g_time_kernel) {
+    VRPX_CUDA(cudaEventRecord(g_ev1, stream));
+    g_ev_valid = true;
+  }
   return VRPX_OK;
 }
 

@@ -22,6 +22,9 @@ EMB = 128
 LAYERS = 3
 
 
+ABI_VERSION = 2  # must equal VRPX_ABI_VERSION of include/vrpx.h
+
+
 class VrpxError(RuntimeError):
     pass
 
@@ -126,10 +129,16 @@ def lib():
     L.vrpx_rollout_workspace_bytes.restype = i64
     L.vrpx_rollout_table_workspace_bytes.argtypes = [i32, i64, i32]
     L.vrpx_rollout_table_workspace_bytes.restype = i64
+    L.vrpx_debug_rollout_profile.argtypes = [C.c_void_p]
+    L.vrpx_debug_rollout_profile.restype = None
+    L.vrpx_debug_rollout_timing.argtypes = [i32]
+    L.vrpx_debug_rollout_timing.restype = None
+    L.vrpx_debug_rollout_kernel_ms.argtypes = []
+    L.vrpx_debug_rollout_kernel_ms.restype = C.c_float
     L.vrpx_rollout.argtypes = [C.POINTER(EnvView), C.POINTER(DecoderWeights), vp, i32, i64, u64, u64, vp, i32, i32,
                                vp, vp, vp, vp, C.POINTER(RolloutTrace), vp, i64, vp]
     L.vrpx_debug_gemm.argtypes = [vp, i64, i32, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp]
-    if L.vrpx_abi_version() != 2:
+    if L.vrpx_abi_version() != ABI_VERSION:
         raise VrpxError("libvrpx.so ABI version mismatch")
     _lib = L
     return L
