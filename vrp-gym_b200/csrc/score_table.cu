@@ -17,16 +17,18 @@ namespace vrpx {
 constexpr int DQK = 48;            // decoder head dim (384 / 8)
 constexpr int QKW = 2 * NH * DQK;  // 768 columns of QK
 
-// One CTA per instance, one warp per head.  The warp stages k'[b, :, head] (N x 48, unpadded: LDS.128 of the B
+// One CTA per instance and half of the heads (grid.y = 2), one warp per head: 4-warp CTAs keep the shared-memory
+// footprint at 43 KB (N = 50) so that five CTAs share an SM and cover the global-load latency.  The warp stages k'[b, :, head] (N x 48, unpadded: LDS.128 of the B
 // fragments is conflict free at a 48-float pitch) in shared memory, streams q' rows from global memory as A fragments
 // and writes S1 rows.  The K axis (48) is permuted so that every thread loads whole float4 chunks: chunk c (0..2) of
 // thread t covers dims 16c + 4t + {0,1,2,3}; k-step 2c + u uses mma k-index t <-> dim 16c+4t+2u and t+4 <-> 16c+4t+2u+1.
 template <int NT8>
-__global__ void __launch_bounds__(256) k_score_table(const float* __restrict__ qk, float* __restrict__ s1, int N) {
+__global__ void __launch_bounds__(128) k_score_table(const float* __restrict__ qk, float* __restrict__ s1, int N) {
   extern __shared__ __align__(16) float ks_all[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = blockIdx.y * 4 + (threadIdx.x >> 5);   // = head
   const int64_t b = blockIdx.x;
-  float* Ks = ks_all + warp * (NT8 * 8 * DQK);
+  float* Ks = ks_all + (threadIdx.x >> 5) * (NT8 * 8 * DQK);
   const float* qkb = qk + b * N * QKW;
   for (int idx = lane; idx < NT8 * 8 * (DQK / 4); idx += 32) {
     const int n = idx / (DQK / 4), c4 = idx % (DQK / 4);
@@ -105,9 +107,9 @@ __global__ void __launch_bounds__(256) k_score_table(const float* __restrict__ q
 
 template <int NT8>
 static int launch_score_table(const float* qk, float* s1, int64_t nb, int N, cudaStream_t stream) {
-  const int smem = NH * NT8 * 8 * DQK * (int)sizeof(float);
+  const int smem = (NH / 2) * NT8 * 8 * DQK * (int)sizeof(float);
   VRPX_CUDA(cudaFuncSetAttribute(k_score_table<NT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_score_table<NT8><<<(unsigned)nb, 256, smem, stream>>>(qk, s1, N);
+  k_score_table<NT8><<<dim3((unsigned)nb, 2), 128, smem, stream>>>(qk, s1, N);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }
