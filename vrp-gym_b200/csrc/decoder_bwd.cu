@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
           QC[m * QC_LD + c] = y;
         }
       } else {
-        tile_gemm_wide_mma_sw<2>(
+        tile_gemm_wide_mma_sw<2, 2>(
             Xs, XS_LD, p.al_t, Wb,
             [&](int m, int c) -> float2 {
               if (m >= cnt) return make_float2(0.f, 0.f);
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
       __syncthreads();
 
       // ---------------- B3: q^ = C · M^T + m_c -> DQ   (partials go through Wb: QC must keep c for the dM update)
-      tile_gemm_tall_mma_sw<2>(QC, QC_LD, p.m_t, Wb, p.m_c, Wb, DQ, XS_LD);   // `part` aliases the weight stage
+      tile_gemm_tall_mma_sw<2, 4, 4>(QC, QC_LD, p.m_t, Wb, p.m_c, Wb, DQ, XS_LD);   // `part` aliases the weight stage
       // ---------------- B4: pointer logits forward + backward: dz, dq^ (-> DQ), dz kept in su for B7
       for (int m = warp; m < TM; m += NT / 32) {
         float4 dqh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
       __syncthreads();
 
       // ---------------- B6: dc = dq^ · M  -> QC (c is dead now)
-      tile_gemm_wide_mma_sw<2>(
+      tile_gemm_wide_mma_sw<2, 2>(
           DQ, XS_LD, p.m_n, Wb, [](int, int) -> float2 { return make_float2(0.f, 0.f); },
           [&](int m, int c, float v0, float v1) { *reinterpret_cast<float2*>(QC + m * QC_LD + c) = make_float2(v0, v1); });
       __syncthreads();
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
         }
         __syncthreads();
         // ---------------- B9: dx_l = dq~ · A_l -> DQ, then dH[b, last] += dx_l
-        tile_gemm_tall_mma_sw<2>(QC, QC_LD, p.al_n, Wb, nullptr, Wb, DQ, XS_LD);
+        tile_gemm_tall_mma_sw<2, 4, 4>(QC, QC_LD, p.al_n, Wb, nullptr, Wb, DQ, XS_LD);
         for (int m = warp; m < cnt; m += NT / 32) {
           if (!s_live[m]) continue;
           const int64_t b = base + m;

@@ -55,7 +55,9 @@ int build_score_table(const float* h, const float* qk_w, int64_t B, int N, float
 constexpr int RMT = 1;
 constexpr int RTM = 16 * RMT;
 constexpr size_t SMEM_X_MMA = smem_x_mma<RMT>(), SMEM_QC_MMA = smem_qc_mma<RMT>();
-constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_MMA;
+constexpr int RNST = 2;   // depth of the per-warp weight rings of the tile GEMMs (tile_gemm.cuh; 3 measured slower)
+constexpr size_t SMEM_W_RING = (size_t)(NT / 32) * RNST * 512 * sizeof(float);   // 64 KiB
+constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_RING;
 
 // Pull one instance's embeddings (N rows of 512 B) towards L2 ahead of their first use in a step: the first pass over
 // h would otherwise pay HBM latency on every row tile.
@@ -106,8 +108,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       *reinterpret_cast<float4*>(Xs + m * XS_LD + lane * 4) = g;
     }
     __syncthreads();
-    tile_gemm_wide_mma<RMT>(                                              // Q~g = A_g · g + a_c
-        Xs, p.w.ag_t, Wb, [&](int, int c) { return *reinterpret_cast<const float2*>(p.w.a_c + c); },
+    tile_gemm_wide_mma_sw<RMT, RNST>(                                              // Q~g = A_g · g + a_c
+        Xs, XS_LD, p.w.ag_t, Wb, [&](int, int c) { return *reinterpret_cast<const float2*>(p.w.a_c + c); },
         [&](int m, int c, float v0, float v1) {
           if (m >= cnt) return;
           const float2 v = make_float2(v0, v1);
@@ -246,8 +248,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         }
       } else {
         if (t == 1 && kind != VRPX_IRP) {
-          tile_gemm_wide_mma<RMT>(                                        // fold `first` (graph_decoder.py:111-113)
-              Xs, p.w.af_t, Wb,
+          tile_gemm_wide_mma_sw<RMT, RNST>(                                        // fold `first` (graph_decoder.py:111-113)
+              Xs, XS_LD, p.w.af_t, Wb,
               [&](int m, int c) {
                 return (m < cnt) ? *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c) : make_float2(0.f, 0.f);
               },
@@ -279,8 +281,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           }
           __syncthreads();
         }
-        tile_gemm_wide_mma<RMT>(                                          // q~ = Q~g (+ load · a_load) + A_l · h[last]
-            Xs, p.w.al_t, Wb,
+        tile_gemm_wide_mma_sw<RMT, RNST>(                                          // q~ = Q~g (+ load · a_load) + A_l · h[last]
+            Xs, XS_LD, p.w.al_t, Wb,
             [&](int m, int c) {
               if (m >= cnt) return make_float2(0.f, 0.f);
               float2 q = *reinterpret_cast<const float2*>(p.qg + (base + m) * QW + c);
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       VRPX_PROF(2)
 
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
-      tile_gemm_tall_mma<RMT>(QC, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
+      tile_gemm_tall_mma_sw<RMT, 8, RNST>(QC, QC_LD, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
 
       // table mode: start copying the next tile's table rows (its `cur` is final: written one step ago, or — when the
       // next tile is this CTA's first tile of the NEXT step — earlier in this step)
