@@ -25,7 +25,7 @@ extern "C" {
 #define VRPX_API
 #endif
 
-#define VRPX_ABI_VERSION 2
+#define VRPX_ABI_VERSION 3
 #define VRPX_MAX_NODES 128 /* visited bitmask = 4 x u32 per instance */
 #define VRPX_EMB 128       /* embedding width E (graph_tsp_agent.py:98) */
 #define VRPX_HEADS 8       /* heads (graph_tsp_agent.py:101, :55) */
@@ -196,6 +196,9 @@ typedef struct vrpx_rollout_trace {
 typedef enum vrpx_rollout_mode { VRPX_GREEDY = 0, VRPX_SAMPLE = 1, VRPX_TEACHER = 2 } vrpx_rollout_mode;
 
 VRPX_API int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N);
+/* Byte offset inside the rollout workspace of the per-episode query table Q~g [B][1024] f32 (read back by the
+ * recompute-based backward); the header in front of it holds the barrier/done counters and the pre-split copy of m_t. */
+VRPX_API int64_t vrpx_rollout_workspace_qg_offset(void);
 /* Workspace size that additionally holds the per-episode glimpse score tables (see qk_w above).  A whole-episode call
  * (t_begin == 0, Tmax >= 3) given at least this much workspace and a non-NULL qk_w runs in table mode. */
 VRPX_API int64_t vrpx_rollout_table_workspace_bytes(int32_t kind, int64_t B, int32_t N);

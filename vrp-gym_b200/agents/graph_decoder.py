@@ -99,7 +99,8 @@ class GraphDecoder(nn.Module):
         env._host_cur = None
         out = {"cost": cost, "logp": logp, "steps": T, "tape": tape[:T], "coupling": G}
         if saved is not None:
-            saved["qg"] = ws[4096:4096 + B * 4096].view(torch.float32).view(B, 1024)  # Q~g incl. the `first` fold (kRolloutSmall = 4096)
+            o = int(L.vrpx_rollout_workspace_qg_offset())
+            saved["qg"] = ws[o:o + B * 4096].view(torch.float32).view(B, 1024)  # Q~g incl. the `first` fold
             saved["ws"] = ws
             out["saved"] = saved
         if logits is not None:

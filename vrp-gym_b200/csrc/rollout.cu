@@ -44,6 +44,7 @@ struct RolloutParams {
   const float* s1;    // [B][N][8][N]  (A_l h[b,l])_head · h[b,n], built before the launch
   float* s0;          // [B][8][N]     Q~g[b]_head · h[b,n], built at step 1 (after the `first` fold)
   float* sl;          // [B][8][N]     IRP: a_load_head · h[b,n]
+  const uint2* m16;   // [512][128] m_t pre-split for the fp16 tensor path (k_split_m16, tile_gemm.cuh)
   int tb_segs;        // table rows staged in shared memory per instance: 0 none, 1 = S1, 2 = S1 + S0, 3 = S1 + S0 + SL
 };
 
@@ -54,8 +55,10 @@ int build_score_table(const float* h, const float* qk_w, int64_t B, int N, float
 // glimpse passes and the pointer-logit pass (all CTAs x tile x 25.6 KB) halves to 60 MB.
 constexpr int RMT = 1;
 constexpr int RTM = 16 * RMT;
-constexpr size_t SMEM_X_MMA = smem_x_mma<RMT>(), SMEM_QC_MMA = smem_qc_mma<RMT>();
-constexpr int RNST = 2;   // depth of the per-warp weight rings of the tile GEMMs (tile_gemm.cuh; 3 measured slower)
+constexpr int RQ_LD = 2 * C16_LD;   // floats per instance slot of QC: the fp16-split c rows of GEMM-B set the stride (1032)
+constexpr size_t SMEM_X_MMA = smem_x_mma<RMT>(), SMEM_QC_MMA = (size_t)RTM * RQ_LD * sizeof(float);
+constexpr int RNST = 2;   // depth of the per-warp weight rings of the tile GEMMs (3 measured slower: the extra 32 KiB of
+                          // shared memory comes out of the L1 that buffers the embedding streams of the other phases)
 constexpr size_t SMEM_W_RING = (size_t)(NT / 32) * RNST * 512 * sizeof(float);   // 64 KiB
 constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_RING;
 
@@ -64,6 +67,14 @@ constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_RING;
 __device__ __forceinline__ void prefetch_instance_l2(const float* hb, int N, int lane) {
   const char* base = reinterpret_cast<const char*>(hb);
   for (int i = lane; i < N * 4; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
+}
+
+// m_t [1024][128] f32 -> M16 [512 k-pairs][128] {hi2, lo2}: the B operand of the fp16-split GEMM-B (tile_gemm.cuh)
+__global__ void k_split_m16(const float* __restrict__ m_t, uint2* __restrict__ m16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // kp * 128 + n
+  if (i >= (QW / 2) * E) return;
+  const int kp = i >> 7, n = i & (E - 1);
+  m16[i] = split_f16x2(m_t[(2 * kp) * E + n], m_t[(2 * kp + 1) * E + n]);
 }
 
 // ---------------------------------------------------------------- the persistent kernel
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           int m = o >> 10, c = o & (QW - 1);
           float y = p.qg[(base + m) * QW + c] + p.w.a_q0[c];
           if (kind == VRPX_IRP) y = fmaf(s_loadf[m], p.w.a_load[c], y);
-          QC[m * QC_LD + c] = y;
+          QC[m * RQ_LD + c] = y;
         }
       } else {
         if (t == 1 && kind != VRPX_IRP) {
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           __syncthreads();
           for (int m = warp; m < cnt; m += NT / 32) {
             const int64_t b = base + m;
-            float* slot = QC + m * QC_LD;
+            float* slot = QC + m * RQ_LD;
             const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
             const int tq = lane & 3;
             for (int i = lane; i < QW / 4; i += 32)
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
               }
               return q;
             },
-            [&](int m, int c, float v0, float v1) { *reinterpret_cast<float2*>(QC + m * QC_LD + c) = make_float2(v0, v1); });
+            [&](int m, int c, float v0, float v1) { *reinterpret_cast<float2*>(QC + m * RQ_LD + c) = make_float2(v0, v1); });
       }
       __syncthreads();
       VRPX_PROF(1)
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       // ---------------- P2: glimpse attention, one warp per instance
       for (int m = warp; m < cnt; m += NT / 32) {
         const int64_t b = base + m;
-        float* slot = QC + m * QC_LD;
+        float* slot = QC + m * RQ_LD;
         const int g = lane >> 2, t = lane & 3;
         const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
         float pr[NH][4];
@@ -431,23 +442,26 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         }
         __syncwarp();  // every lane is done reading P before c overwrites the slot
         // C fragment of m-tile j = 2cq+u: [0] (dim d, head 2t), [1] (dim d, head 2t+1), [2] (dim d+1, head 2t),
-        // [3] (dim d+1, head 2t+1) with d = 32cq + 4g + 2u  ->  c[head][dim] for GEMM-B
+        // [3] (dim d+1, head 2t+1) with d = 32cq + 4g + 2u  ->  the A operand of GEMM-B, pre-split for the fp16 tensor
+        // path (tile_gemm.cuh): row m of C16, k = head * 128 + dim; per head and cq one 16-byte chunk = the two k-pairs
+        // (d0, d0+1), (d0+2, d0+3), d0 = 32cq + 4g, at the swizzled chunk (head*32 + 8cq + g) ^ (t << 1)
+        uint4* crow = reinterpret_cast<uint4*>(slot);
 #pragma unroll
         for (int cq = 0; cq < 4; ++cq)
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int d = 32 * cq + 4 * g + 2 * u, j = 2 * cq + u;
-            *reinterpret_cast<float2*>(slot + (2 * t) * E + d) = make_float2(cacc[j][0], cacc[j][2]);
-            *reinterpret_cast<float2*>(slot + (2 * t + 1) * E + d) = make_float2(cacc[j][1], cacc[j][3]);
+          for (int e = 0; e < 2; ++e) {
+            const uint2 p01 = split_f16x2(cacc[2 * cq][e], cacc[2 * cq][e + 2]);           // dims d0, d0+1 of head 2t+e
+            const uint2 p23 = split_f16x2(cacc[2 * cq + 1][e], cacc[2 * cq + 1][e + 2]);   // dims d0+2, d0+3
+            crow[(((2 * t + e) * 32 + 8 * cq + g) ^ (t << 1))] = make_uint4(p01.x, p01.y, p23.x, p23.y);
           }
       }
       // rows >= cnt of C must be finite for GEMM-B (results unused): zero them
-      for (int o = cnt * QW + tid; o < RTM * QW; o += NT) QC[(o >> 10) * QC_LD + (o & (QW - 1))] = 0.f;
+      for (int o = cnt * QW + tid; o < RTM * QW; o += NT) QC[(o >> 10) * RQ_LD + (o & (QW - 1))] = 0.f;
       __syncthreads();
       VRPX_PROF(2)
 
       // ---------------- P3: q^ = C · M^T + m_c  -> Xs
-      tile_gemm_tall_mma_sw<RMT, 8, RNST>(QC, QC_LD, p.w.m_t, Wb, p.w.m_c, QC, Xs, XS_LD);
+      tile_gemm_tall_f16<RNST>(reinterpret_cast<const uint2*>(QC), p.m16, Wb, p.w.m_c, QC, Xs, XS_LD);
 
       // table mode: start copying the next tile's table rows (its `cur` is final: written one step ago, or — when the
       // next tile is this CTA's first tile of the NEXT step — earlier in this step)
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
       bool unfinished = false;
       for (int m = warp; m < cnt; m += NT / 32) {
         const int64_t b = base + m;
-        float* slot = QC + m * QC_LD;  // free scratch again
+        float* slot = QC + m * RQ_LD;  // free scratch again
         const float4 qh = *reinterpret_cast<const float4*>(Xs + m * XS_LD + lane * 4);
         const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
         {
@@ -616,6 +630,8 @@ static int g_time_kernel = 0;                        // vrpx_debug_rollout_timin
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static bool g_ev_valid = false;
 constexpr int64_t kRolloutSmall = 4096;  // barrier counter + notdone[<=513]
+constexpr int64_t kRolloutM16 = (int64_t)(QW / 2) * E * sizeof(uint2);   // 512 KiB: pre-split m_t
+constexpr int64_t kRolloutHdr = kRolloutSmall + kRolloutM16;             // Q~g follows
 
 }  // namespace vrpx
 
@@ -640,8 +656,10 @@ float vrpx_debug_rollout_kernel_ms(void) {
 
 int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N) {
   (void)N;
-  return kRolloutSmall + B * (int64_t)QW * (int64_t)sizeof(float);
+  return kRolloutHdr + B * (int64_t)QW * (int64_t)sizeof(float);
 }
+
+int64_t vrpx_rollout_workspace_qg_offset(void) { return kRolloutHdr; }
 
 // table-mode workspace: header | Q~g | S0 | SL (IRP) | S1 | QK slice, every segment 256-byte aligned
 namespace {
@@ -652,7 +670,7 @@ inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 TableLayout table_layout(int kind, int64_t B, int N) {
   TableLayout L;
   const int64_t f = (int64_t)sizeof(float);
-  L.s0 = align256(kRolloutSmall + B * QW * f);
+  L.s0 = align256(kRolloutHdr + B * QW * f);
   L.sl = align256(L.s0 + B * NH * N * f);
   L.s1 = (kind == VRPX_IRP) ? align256(L.sl + B * NH * N * f) : L.sl;
   L.qk = align256(L.s1 + B * N * NH * N * f);
@@ -678,6 +696,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   VRPX_CHECK_ARG(Tmax >= 1 && Tmax <= 1000 && t_begin >= 0, "t_begin / Tmax out of range");
   VRPX_CHECK_ARG(coupling >= 0, "coupling must be >= 0");
   VRPX_CHECK_ARG(ws_bytes >= vrpx_rollout_workspace_bytes(env->B, env->N), "workspace too small");
+  VRPX_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
   VRPX_CHECK_ARG(w->ag_t && w->al_t && w->a_c && w->a_q0 && w->m_t && w->m_c, "decoder weights");
   VRPX_CHECK_ARG(env->kind == VRPX_IRP ? (w->a_load != nullptr) : (w->af_t != nullptr), "decoder weights (kind)");
 
@@ -702,7 +721,8 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   p.prof = g_rollout_prof;
   p.bar = reinterpret_cast<unsigned*>(ws);
   p.notdone = reinterpret_cast<int*>(ws) + 8;
-  p.qg = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kRolloutSmall);
+  p.qg = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kRolloutHdr);
+  p.m16 = reinterpret_cast<const uint2*>(reinterpret_cast<char*>(ws) + kRolloutSmall);
   p.s1 = nullptr;
   p.s0 = p.sl = nullptr;
   // table mode: whole-episode call with the large workspace and the rank-48 factors
@@ -731,6 +751,8 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   VRPX_CHECK_ARG((int64_t)(Tmax + 1 + 8) * 4 <= kRolloutSmall, "Tmax too large for workspace header");
 
   VRPX_CUDA(cudaMemsetAsync(ws, 0, kRolloutSmall, stream));
+  k_split_m16<<<(QW / 2) * E / 256, 256, 0, stream>>>(w->m_t, reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + kRolloutSmall));
+  VRPX_LAUNCH_CHECK();
   VRPX_CUDA(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
   int64_t ntiles = (env->B + RTM - 1) / RTM;
   int grid = (int)((ntiles < (int64_t)num_sms()) ? ntiles : (int64_t)num_sms());

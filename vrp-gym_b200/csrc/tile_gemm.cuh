@@ -2,6 +2,8 @@
 // recompute-based decoder backward (decoder_bwd.cu): tiles of 16 or 32 instances, 512 threads, tile GEMMs on the
 // warp-level tensor path (mma.sync TF32, 3-term split) with per-warp weight streams from L2 (cp.async rings).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "env_rules.cuh"
 
 namespace vrpx {
@@ -216,15 +218,121 @@ __device__ __forceinline__ void tile_gemm_tall_mma_sw(const float* __restrict__ 
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c = ng * NCW + 8 * j + 2 * t;
+      // columns XOR-swizzled by the row (bits 3-4) so that the 8 rows a warp stores at once fall into distinct banks
+      const int c = (ng * NCW + 8 * j + 2 * t) ^ ((g & 3) << 3);
       *reinterpret_cast<float2*>(part + (kg * TMm + mt * 16 + g) * E + c) = make_float2(acc[mt][j][0], acc[mt][j][1]);
       *reinterpret_cast<float2*>(part + (kg * TMm + mt * 16 + g + 8) * E + c) = make_float2(acc[mt][j][2], acc[mt][j][3]);
     }
   __syncthreads();
   for (int o = tid; o < TMm * E; o += NT) {
     float s = 0.f;
+    const int os = o ^ (((o >> 7) & 3) << 3);
 #pragma unroll
-    for (int k = 0; k < KG; ++k) s += part[k * TMm * E + o];
+    for (int k = 0; k < KG; ++k) s += part[k * TMm * E + os];
+    out[(o >> 7) * out_ld + (o & (E - 1))] = s + (bias ? bias[o & (E - 1)] : 0.f);
+  }
+  __syncthreads();
+}
+
+// ================================================================ fp16-split tile GEMM (rollout GEMM-B)
+// Same ~fp32 accuracy as the 3xTF32 scheme at HALF the tensor-pipe time: mma.sync.m16n8k16 (f16 in, f32 accumulate)
+// issues at the rate of the TF32 m16n8k8 but covers twice the k range (tools/mma_bench3.cu: 958 vs 479 MAC/clk/SM).
+// Every fp32 operand x is carried as two halves  hi = f16(x),  lo = f16((x - hi) * 2^11)  — 22 significant bits like
+// the TF32 hi/lo pair (the 2^11 scale keeps lo in the normal f16 range whenever hi is).  hi·hi accumulates in one f32
+// accumulator, lo·hi + hi·lo in a second one that is folded in with 2^-11 at the end; lo·lo (2^-22) is dropped.
+// Operands must be below 65504 in magnitude (embeddings after BatchNorm and folded weights are O(10) at most).
+// Both operands are stored PRE-SPLIT as {hi2, lo2} = 8 bytes per pair of consecutive k, which is what one register of
+// the m16n8k16 fragments holds, so the k loop has no conversion arithmetic at all: one LDS.64 per fragment register pair.
+__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr float F16_LO_SCALE = 2048.0f;
+__device__ __forceinline__ uint2 split_f16x2(float x0, float x1) {   // {hi(x0) hi(x1), lo(x0) lo(x1)}
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * F16_LO_SCALE, (x1 - hf.y) * F16_LO_SCALE);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&h), *reinterpret_cast<const uint32_t*>(&l));
+}
+
+// A operand of the fp16-split tall GEMM: C16[16][C16_LD] uint2, element (m, kp) = split pair (k = 2kp, 2kp + 1) of row m,
+// stored at column kp ^ (((kp >> 7) & 3) << 2).  The XOR (by the head pair the k-pair belongs to) lets the producer
+// (rollout.cu, glimpse value pass: lanes of equal g and different t write different head pairs) store 16-byte chunks
+// without bank conflicts; C16_LD = 4 (mod 16) keeps the fragment reads (row g, k-pair t) conflict free.
+constexpr int C16_LD = QW / 2 + 4;   // 516 uint2 = 1032 floats per row
+__device__ __forceinline__ int c16_col(int kp) { return kp ^ (((kp >> 7) & 3) << 2); }
+
+// out[16][128] (ld out_ld) = C[16][1024] · M[1024][128] + bias with pre-split operands.  M16: global [512 k-pairs][128]
+// uint2.  16 warps: warp (kg = w / 4, ng = w % 4) owns columns [32 ng, +32) over k-pairs [128 kg, +128); each streams its
+// slice through a private cp.async ring of NST stages of [8 k-pairs][32 columns] uint2 (2 KiB; column c of row r at
+// c ^ ((r & 3) << 2): fragment reads (k-pair t, column g) conflict free).  part: [4][16][128] floats, may alias C16.
+// Measured (C4): this loop is bound by the L2 -> SM stream of the weights (512 KiB per 16-instance tile on every SM at
+// once), not by the tensor pipe or the issue slots: a leaner k loop (vector fragment loads, no register moves) and a
+// deeper ring both left its time unchanged.
+template <int NST>
+__device__ __forceinline__ void tile_gemm_tall_f16(const uint2* __restrict__ C16, const uint2* __restrict__ M16,
+                                                   float* __restrict__ Wb, const float* __restrict__ bias,
+                                                   float* __restrict__ part, float* __restrict__ out, int out_ld) {
+  constexpr int KG = 4, NG = 4, NJ = 4, KPW = (QW / 2) / KG, NKS = KPW / 8, STAGE = 8 * 32;   // STAGE in uint2
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int kg = warp / NG, ng = warp % NG;
+  uint2* wbuf = reinterpret_cast<uint2*>(Wb) + warp * NST * STAGE;
+  const uint2* src = M16 + (size_t)(kg * KPW) * E + ng * 32;
+  auto stage = [&](int ks, uint2* dst) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = lane + 32 * i, r = idx >> 4, c2 = idx & 15;
+      cp_async16(dst + r * 32 + ((2 * c2) ^ ((r & 3) << 2)), src + (size_t)(ks * 8 + r) * E + 2 * c2);
+    }
+  };
+  float ahh[NJ][4], amx[NJ][4];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ahh[j][i] = amx[j][i] = 0.f;
+#pragma unroll
+  for (int s = 0; s < NST - 1; ++s) {
+    if (s < NKS) stage(s, wbuf + s * STAGE);
+    cp_async_commit();
+  }
+  const uint2* row0 = C16 + g * C16_LD;
+  const uint2* row1 = C16 + (g + 8) * C16_LD;
+  for (int ks = 0; ks < NKS; ++ks) {
+    if (ks + NST - 1 < NKS) stage(ks + NST - 1, wbuf + ((ks + NST - 1) % NST) * STAGE);
+    cp_async_commit();
+    cp_async_wait<NST - 1>();
+    __syncwarp();
+    const int kp0 = kg * KPW + ks * 8;
+    const int ca = c16_col(kp0 + t), cb = c16_col(kp0 + t + 4);
+    const uint2 a0 = row0[ca], a1 = row1[ca], a2 = row0[cb], a3 = row1[cb];
+    const uint32_t ah[4] = {a0.x, a1.x, a2.x, a3.x}, al[4] = {a0.y, a1.y, a2.y, a3.y};
+    const uint2* wb = wbuf + (ks % NST) * STAGE;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = (8 * j + g) ^ (t << 2);
+      const uint2 b0 = wb[t * 32 + c], b1 = wb[(t + 4) * 32 + c];
+      mma_f16_16x8x16(ahh[j], ah, b0.x, b1.x);
+      mma_f16_16x8x16(amx[j], al, b0.x, b1.x);
+      mma_f16_16x8x16(amx[j], ah, b0.y, b1.y);
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int c = (ng * 32 + 8 * j + 2 * t) ^ ((g & 3) << 3);   // same row swizzle as tile_gemm_tall_mma_sw
+    const float sc = 1.0f / F16_LO_SCALE;
+    *reinterpret_cast<float2*>(part + (kg * 16 + g) * E + c) = make_float2(fmaf(amx[j][0], sc, ahh[j][0]), fmaf(amx[j][1], sc, ahh[j][1]));
+    *reinterpret_cast<float2*>(part + (kg * 16 + g + 8) * E + c) = make_float2(fmaf(amx[j][2], sc, ahh[j][2]), fmaf(amx[j][3], sc, ahh[j][3]));
+  }
+  __syncthreads();
+  for (int o = tid; o < 16 * E; o += NT) {
+    float s = 0.f;
+    const int os = o ^ (((o >> 7) & 3) << 3);
+#pragma unroll
+    for (int k = 0; k < KG; ++k) s += part[k * 16 * E + os];
     out[(o >> 7) * out_ld + (o & (E - 1))] = s + (bias ? bias[o & (E - 1)] : 0.f);
   }
   __syncthreads();

@@ -22,7 +22,7 @@ EMB = 128
 LAYERS = 3
 
 
-ABI_VERSION = 2  # must equal VRPX_ABI_VERSION of include/vrpx.h
+ABI_VERSION = 3  # must equal VRPX_ABI_VERSION of include/vrpx.h
 
 
 class VrpxError(RuntimeError):
@@ -127,6 +127,8 @@ def lib():
     L.vrpx_episode_scatter.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.vrpx_rollout_workspace_bytes.argtypes = [i64, i32]
     L.vrpx_rollout_workspace_bytes.restype = i64
+    L.vrpx_rollout_workspace_qg_offset.argtypes = []
+    L.vrpx_rollout_workspace_qg_offset.restype = i64
     L.vrpx_rollout_table_workspace_bytes.argtypes = [i32, i64, i32]
     L.vrpx_rollout_table_workspace_bytes.restype = i64
     L.vrpx_debug_rollout_profile.argtypes = [C.c_void_p]
