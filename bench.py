@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak scaling)")
     ap.add_argument("--coupling", type=int, default=-1, help="glimpse-mask coupling group; -1 = whole per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="instances in the bounded CPU sample")
-    ap.add_argument("--gemm-path", type=int, default=0, help="0 tcgen05 3xTF32, 1 fp32 SIMT")
+    ap.add_argument("--gemm-path", type=int, default=0, help="0 tcgen05 f16-split (production), 1 fp32 SIMT, 2 tcgen05 3xTF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=69)
     ap.add_argument("--mode", default="rollout", choices=["rollout", "train"],
@@ -342,7 +342,7 @@ def main():
         line = {
             "metric": "instance_steps_per_sec", "value": value, "unit": "instance-steps/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (encoder GEMMs 3xTF32 on tcgen05; env f64/bitmask)"
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor-core contractions on f16 hi/lo splits with f32 accumulation, ~fp32 accuracy; env f64/bitmask)"
             if a.gemm_path == 0 else "f32", "data": "synthetic",
             "config": {"workload": f"greedy {a.kind.upper()}-{N} rollout (encoder + {T} fused decode/env steps), "
                                    f"{B} Philox-uniform instances per GPU, seed-initialised {a.kind.upper()}Agent weights",

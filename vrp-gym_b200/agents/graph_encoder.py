@@ -84,7 +84,7 @@ class GraphEncoder(nn.Module):
         self.attention_layers = nn.ModuleList(
             [MultiHeadAttentionLayer(embedding_dim=embedding_dim, hidden_dim=hidden_dim, num_heads=num_heads)
              for _ in range(num_attention_layers)])
-        self.gemm_path = 0  # 0: tcgen05 3xTF32, 1: fp32 SIMT cross-check
+        self.gemm_path = 0  # 0: tcgen05 f16-split, 1: fp32 SIMT cross-check, 2: tcgen05 3xTF32
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x (num_graphs, num_nodes, f) -> embeddings (num_graphs, num_nodes, 128), on x's device."""

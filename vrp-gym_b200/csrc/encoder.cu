@@ -1,7 +1,7 @@
 // encoder.cu — GraphEncoder / GraphDemandEncoder forward (agents/graph_encoder.py:41-58, :95-138,
 // :141-154, :183-198): node/depot embedding, 3 x { MHA + skip + BN, FF + skip + BN }.
 //
-// Dense contractions go through gemm_tc (tcgen05, 3xTF32) or gemm_simt (fp32 FFMA cross-check);
+// Dense contractions go through gemm_tc (tcgen05, f16 hi/lo split) or gemm_simt (fp32 FFMA cross-check);
 // the per-instance N x N attention (dh = 16) and the BatchNorm reductions are SIMT kernels here.
 #include "gemm.cuh"
 

@@ -1,5 +1,5 @@
 // gemm.cuh — internal GEMM interface shared by the SIMT cross-check path (encoder.cu) and the
-// tcgen05 3xTF32 tensor-core path (gemm_tc.cu).
+// tcgen05 tensor-core paths (gemm_tc4.cu, gemm_tc3.cu).
 #pragma once
 #include "common.cuh"
 
@@ -22,13 +22,14 @@ struct GemmArgs {
   const float* gate = nullptr;  // [R][NOUT] or nullptr: ReLU-backward gate (acc is zeroed where gate <= 0)
 };
 
-int gemm_simt(const GemmArgs& a, cudaStream_t stream);  // fp32 FFMA, smem tiled
-int gemm_tc(const GemmArgs& a, cudaStream_t stream);    // tcgen05.mma kind::tf32, 3-term split (≈fp32); persistent, TMA-staged, A operand in TMEM (gemm_tc3.cu)
-int gemm_tc_v1(const GemmArgs& a, cudaStream_t stream); // first-generation tcgen05 kernel (gemm_tc.cu), cross-check
-int gemm_tc_v2(const GemmArgs& a, cudaStream_t stream); // persistent TMA kernel with both operands in smem (gemm_tc2.cu)
+int gemm_simt(const GemmArgs& a, cudaStream_t stream);     // fp32 FFMA, smem tiled (encoder.cu)
+int gemm_tc(const GemmArgs& a, cudaStream_t stream);       // production: tcgen05.mma kind::f16 on f16 hi/lo halves (≈fp32), persistent,
+                                                           // TMA-staged, A operand in TMEM (gemm_tc4.cu)
+int gemm_tc_tf32(const GemmArgs& a, cudaStream_t stream);  // previous generation: kind::tf32 3-term split (gemm_tc3.cu), cross-check
 
+// path: 0 tcgen05 f16-split (production), 1 fp32 SIMT, 2 tcgen05 3xTF32
 inline int gemm_dispatch(int path, const GemmArgs& a, cudaStream_t stream) {
-  return path == 0 ? gemm_tc(a, stream) : (path == 2 ? gemm_tc_v1(a, stream) : (path == 3 ? gemm_tc_v2(a, stream) : gemm_simt(a, stream)));
+  return path == 0 ? gemm_tc(a, stream) : (path == 2 ? gemm_tc_tf32(a, stream) : gemm_simt(a, stream));
 }
 
 }  // namespace vrpx

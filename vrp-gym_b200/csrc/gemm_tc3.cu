@@ -1,14 +1,15 @@
 // gemm_tc3.cu — persistent, warp-specialised tcgen05 GEMM (3xTF32): TMA-staged tiles, A operand fed from TMEM.
 //
-// Same pipeline as gemm_tc2.cu, with one change that removes the shared-memory bandwidth ceiling measured there
-// (l1tex 60-75 % busy, tensor pipe 12-30 %): a 128x128xK=8 tf32 MMA reads 4 KiB of A and 4 KiB of B from smem every
+// Superseded as the production path by gemm_tc4.cu (f16-split, half the tensor time); kept as the 3xTF32 cross-check.
+// The A operand lives in TMEM because with both operands in shared memory the port saturates (measured on the
+// generation before: l1tex 60-75 % busy, tensor pipe 12-30 %): a 128x128xK=8 tf32 MMA reads 4 KiB of A and 4 KiB of B from smem every
 // 64 cycles, which by itself saturates the 128 B/clk shared-memory port once the converters' traffic is added.  Here
 // the converter warps write the hi / lo halves of the X tile straight into TENSOR MEMORY (tcgen05.st, lane = tile row,
 // one 32-bit column per k element) and the MMAs take A from TMEM, so shared memory only carries the raw TMA tiles
 // and the B (weight) operand.
 //
-//   Y[R][NOUT] = epilogue( X[R][K] · W[NOUT][K]^T ),  fp32 in / fp32 out, ~fp32 accuracy (see gemm_tc.cu for the
-//   precision policy: D = Xlo·Whi + Xhi·Wlo + Xhi·Whi on tcgen05.mma kind::tf32, fp32 accumulators in TMEM).
+//   Y[R][NOUT] = epilogue( X[R][K] · W[NOUT][K]^T ),  fp32 in / fp32 out, ~fp32 accuracy (precision
+//   policy: hi = x & 0xffffe000, lo = x - hi; D = Xlo·Whi + Xhi·Wlo + Xhi·Whi on tcgen05.mma kind::tf32, fp32 in TMEM).
 //
 // One CTA per SM loops over 128x128 output tiles (column tile fastest, so the CTAs that share an X row tile run
 // side by side and hit L2).  Roles (12 warps):
@@ -63,7 +64,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major SWIZZLE_128B, SBO 1024 B (gemm_tc.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major SWIZZLE_128B, SBO 1024 B
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)1 << 16;
@@ -355,7 +356,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int cols) {
 
 }  // namespace tc3
 
-int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
+int gemm_tc_tf32(const GemmArgs& a, cudaStream_t stream) {  // previous production path, kept as a cross-check
   using namespace tc3;
   if (a.K % BK != 0 || a.NOUT % BN != 0 || a.R <= 0) {
     set_error("gemm_tc: unsupported shape R=%lld K=%d NOUT=%d", (long long)a.R, a.K, a.NOUT);

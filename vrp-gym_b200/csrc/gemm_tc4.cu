@@ -1,0 +1,458 @@
+// gemm_tc4.cu — persistent, warp-specialised tcgen05 GEMM on the fp16-split tensor path (kind::f16), ~fp32 accuracy.
+//
+//   Y[R][NOUT] = epilogue( X[R][K] · W[NOUT][K]^T ),  fp32 in / fp32 out.
+//
+// Precision policy: every fp32 operand is carried as two halves, hi = f16(x) and lo = f16(x - hi) (22 significant bits,
+// like the TF32 hi/lo pair of gemm_tc3.cu), and  D = Xlo·Whi + Xhi·Wlo + Xhi·Whi  accumulates in fp32 TMEM.  A kind::f16
+// MMA covers K = 16 per instruction at the issue rate of a kind::tf32 MMA with K = 8, and reads the same bytes of shared
+// memory per instruction: half the tensor time and half the operand traffic of 3xTF32.  W is scaled by 2^8 before the
+// split so that its lo halves stay in the normal f16 range (the epilogue multiplies by 2^-8); activations are O(1).
+// Operands must stay below 65504 / 2^8 (weights) and 65504 (activations) in magnitude.
+//
+// Pipeline (gemm_tc3.cu's, with 64-wide k blocks and no shared-memory rewriting):
+//   k_split_w16  W -> Whi | Wlo (f16, [NOUT][K]) once per call (W is at most 512 x 512)
+//   warp 4      TMA producer: per stage two raw fp32 X boxes (32 floats x 128 rows) + the Whi and Wlo boxes (64 halves x
+//               128 rows), all SWIZZLE_128B
+//   warps 0-3   converters: thread = tile row; split the row's 64 floats and write the packed halves straight into TENSOR
+//               MEMORY (tcgen05.st: 32 hi + 32 lo columns per stage) — the MMAs take A from TMEM
+//   warp 5      MMA issuer: 12 tcgen05.mma per 64-wide k block; tcgen05.commit releases the stage
+//   warps 8-15  epilogue from one of TWO TMEM accumulators while the other is being filled
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "gemm.cuh"
+
+namespace vrpx {
+namespace tc4 {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 512;
+constexpr int TILE_BYTES = 16 * 1024;          // every TMA box: 128 rows x 128 bytes
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // X raw k 0..31 | X raw k 32..63 | W hi | W lo   (X hi/lo live in TMEM)
+constexpr uint32_t TMEM_A0 = 2 * BN;            // TMEM columns: 2 accumulators, then STAGES x (32 hi + 32 lo) A columns
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 + 1024;   // stages | 8 epilogue transpose patches | alignment slack
+// kind::f16: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr float W_SCALE = 256.0f, X_SCALE = 256.0f, OUT_SCALE = 1.0f / (W_SCALE * X_SCALE);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major SWIZZLE_128B, SBO 1024 B (gemm_tc.cu)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+// {f16(x0) f16(x1)} and the f16 pair of the remainders
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  x0 *= X_SCALE;
+  x1 *= X_SCALE;
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Row r (= converter thread) of the two raw X boxes of a stage (64 floats, 16 swizzled 16-byte chunks) -> 32 packed hi
+// + 32 packed lo words in TMEM lane r (column c holds k = 2c, 2c + 1).
+__device__ __forceinline__ void x_tile_to_tmem(const unsigned char* raw, int r, uint32_t taddr_hi) {
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int half = 0; half < 2; ++half)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(raw + half * TILE_BYTES + r * 128 + ((c ^ (r & 7)) << 4));
+      split_pair(v.x, v.y, hi[half * 16 + 2 * c], lo[half * 16 + 2 * c]);
+      split_pair(v.z, v.w, hi[half * 16 + 2 * c + 1], lo[half * 16 + 2 * c + 1]);
+    }
+  tmem_st32(taddr_hi, hi);
+  tmem_st32(taddr_hi + 32, lo);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// W [n] f32 -> f16 hi | lo of W * 2^8
+__global__ void k_split_w16(const float* __restrict__ W, __half* __restrict__ hi, __half* __restrict__ lo, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = W[i] * W_SCALE;
+  const __half h = __float2half_rn(x);
+  hi[i] = h;
+  lo[i] = __float2half_rn(x - __half2float(h));
+}
+
+template <bool RES, bool GATE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh,
+           const __grid_constant__ CUtensorMap mapWl) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t s_raw_full[STAGES], s_conv_done[STAGES], s_stage_free[STAGES], s_acc_full[2], s_acc_free[2];
+  __shared__ uint32_t s_tmem;
+  // 1 KiB alignment (SWIZZLE_128B atoms) by an OFFSET into the extern array: pointer arithmetic keeps the shared address
+  // space, so the converters and the epilogue get LDS / STS instead of generic loads and stores
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nct = a.NOUT / BN;
+  const int64_t nrt = (a.R + BM - 1) / BM;
+  // Every CTA keeps ONE column tile (ct) for its whole life and strides over the row tiles: the epilogue's per-column
+  // constants (bias, folded BatchNorm scale / shift) are loaded once, and the CTAs that share an X row tile (consecutive
+  // blockIdx) still run side by side and hit L2.  gridDim.x is a multiple of nct (host side).
+  const int ct = (int)(blockIdx.x % nct), col0 = ct * BN;
+  const int64_t rt0 = blockIdx.x / nct, rts = gridDim.x / nct;
+  const int nkb = a.K / BK;
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&s_raw_full[i]), 1);
+      mbar_init(smem_u32(&s_conv_done[i]), 4);
+      mbar_init(smem_u32(&s_stage_free[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_acc_full[i]), 1);
+      mbar_init(smem_u32(&s_acc_free[i]), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t kbc = 0;
+      for (int64_t rt = rt0; rt < nrt; rt += rts) {
+        const int row0 = (int)rt * BM;
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
+          mbar_wait(smem_u32(&s_stage_free[s]), ph ^ 1);
+          unsigned char* st = smem + s * STAGE_BYTES;
+          const uint32_t bar = smem_u32(&s_raw_full[s]);
+          mbar_expect_tx(bar, STAGE_BYTES);
+          tma_load_2d(smem_u32(st), &mapX, kb * BK, row0, bar);
+          tma_load_2d(smem_u32(st + TILE_BYTES), &mapX, kb * BK + 32, row0, bar);
+          tma_load_2d(smem_u32(st + 2 * TILE_BYTES), &mapWh, kb * BK, col0, bar);
+          tma_load_2d(smem_u32(st + 3 * TILE_BYTES), &mapWl, kb * BK, col0, bar);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== converters =====================
+    uint32_t kbc = 0;
+    for (int64_t rt = rt0; rt < nrt; rt += rts) {
+      for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+        const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
+        unsigned char* st = smem + s * STAGE_BYTES;
+        mbar_wait(smem_u32(&s_raw_full[s]), ph);
+        x_tile_to_tmem(st, tid, tmem + ((uint32_t)(warp * 32) << 16) + TMEM_A0 + s * 64);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_conv_done[s]));
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t kbc = 0, ti = 0;
+      for (int64_t rt = rt0; rt < nrt; rt += rts, ++ti) {
+        const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+        mbar_wait(smem_u32(&s_acc_free[acc]), aph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
+          unsigned char* st = smem + s * STAGE_BYTES;
+          mbar_wait(smem_u32(&s_conv_done[s]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ah = tmem + TMEM_A0 + s * 64, alo = ah + 32;
+          const uint64_t wh = make_desc(smem_u32(st + 2 * TILE_BYTES)), wl = make_desc(smem_u32(st + 3 * TILE_BYTES));
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {   // k16 step: 8 TMEM columns of A, 32 bytes along the swizzled W rows
+            const uint64_t o = (uint64_t)(2 * j);
+            mma_f16_ts(d, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u);
+            mma_f16_ts(d, ah + 8 * j, wl + o, 1u);
+            mma_f16_ts(d, ah + 8 * j, wh + o, 1u);
+          }
+          mma_commit(smem_u32(&s_stage_free[s]));
+        }
+        mma_commit(smem_u32(&s_acc_full[acc]));
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue =====================
+    // tcgen05.ld hands every thread one tile ROW (32 consecutive columns).  Storing that directly would touch 32
+    // different 128-byte lines per instruction, so each 32x32 chunk is transposed through a 4 KiB swizzled smem patch:
+    // afterwards lane l owns columns 4(l&7)..+3 of rows 4i + (l>>3), i = 0..7, and every global load / store
+    // instruction of the warp covers 4 rows x 128 contiguous bytes.
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int chalf = (warp - 8) >> 2;   // this warp's pair of 32-column chunks
+    unsigned char* patch = smem + STAGES * STAGE_BYTES + (warp - 8) * 4096;
+    const int lr = lane >> 3, lc = lane & 7;
+    const float relu_floor = a.relu ? 0.f : -INFINITY;
+    // per-column epilogue constants of this warp's two 32-column chunks (4 columns per lane after the transpose)
+    float4 bias4[2], sc4[2], sh4[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = col0 + (2 * chalf + k) * 32 + lc * 4;
+      bias4[k] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sc4[k] = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      sh4[k] = a.scale ? __ldg(reinterpret_cast<const float4*>(a.shift + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t ti = 0;
+    for (int64_t rt = rt0; rt < nrt; rt += rts, ++ti) {
+      const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+      const int64_t row_base = rt * BM + q * 32;
+      mbar_wait(smem_u32(&s_acc_full[acc]), aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int cc = 2 * chalf + k;
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * BN + cc * 32;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        const int c = col0 + cc * 32 + lc * 4;   // this lane's 4 columns after the transpose
+        // the (coalesced) residual / gate rows are fetched while the TMEM load is in flight
+        float4 res[8], gt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = row_base + 4 * i + lr;
+          if (RES) res[i] = (r < a.R) ? *reinterpret_cast<const float4*>(a.residual + r * a.NOUT + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (GATE) gt[i] = (r < a.R) ? *reinterpret_cast<const float4*>(a.gate + r * a.NOUT + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (k == 1) {
+          // both chunks are in registers: the accumulator can be refilled while this warp finishes its stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_acc_free[acc]));
+        }
+        __syncwarp();  // the previous chunk's reads of the patch are complete
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4)
+          *reinterpret_cast<uint4*>(patch + lane * 128 + ((g4 ^ (lane & 7)) << 4)) = make_uint4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+        __syncwarp();
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + lr;
+          x[i] = *reinterpret_cast<const float4*>(patch + rr * 128 + ((lc ^ (rr & 7)) << 4));
+        }
+        const float bb[4] = {bias4[k].x, bias4[k].y, bias4[k].z, bias4[k].w}, ss[4] = {sc4[k].x, sc4[k].y, sc4[k].z, sc4[k].w},
+                    hh[4] = {sh4[k].x, sh4[k].y, sh4[k].z, sh4[k].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = row_base + 4 * i + lr;
+          float y[4] = {x[i].x * OUT_SCALE, x[i].y * OUT_SCALE, x[i].z * OUT_SCALE, x[i].w * OUT_SCALE};
+          const float gg[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w}, rs[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (GATE) y[e] = (gg[e] > 0.f) ? y[e] : 0.f;
+            y[e] = fmaxf(y[e] + bb[e], relu_floor);
+            if (RES) y[e] += rs[e];
+            y[e] = fmaf(y[e], ss[e], hh[e]);
+          }
+          if (r < a.R) *reinterpret_cast<float4*>(a.Y + r * a.NOUT + c) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major matrix [rows][cols] -> boxes of 128 bytes x 128 rows (32 floats or 64 halves), SWIZZLE_128B, zero fill
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, bool f16) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled entry point not available");
+    return VRPX_ERR_CUDA;
+  }
+  const size_t es = f16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d", (int)r, (long long)rows, cols);
+    return VRPX_ERR_CUDA;
+  }
+  return VRPX_OK;
+}
+
+// Scratch for the split weights: one 4 MiB buffer per (device, stream), allocated on first use and kept for the life of
+// the process.  Calls on one stream are ordered (the split kernel of call n+1 runs after the GEMM of call n), calls on
+// different streams get different buffers.  (cudaMallocAsync per call was measured 10x slower end to end: the default
+// pool returns its memory at every synchronisation.)
+constexpr int kMaxSplitWeights = 1 << 20;
+static __half* split_scratch(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, __half*> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, stream);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  void* p = nullptr;
+  if (cudaMalloc(&p, (size_t)2 * kMaxSplitWeights * sizeof(__half)) != cudaSuccess) {
+    set_error("gemm_tc: cudaMalloc of the weight-split scratch failed");
+    return nullptr;
+  }
+  cache[key] = static_cast<__half*>(p);
+  return static_cast<__half*>(p);
+}
+
+}  // namespace tc4
+
+int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
+  using namespace tc4;
+  if (a.K % BK != 0 || a.NOUT % BN != 0 || a.R <= 0) {
+    set_error("gemm_tc: unsupported shape R=%lld K=%d NOUT=%d", (long long)a.R, a.K, a.NOUT);
+    return VRPX_ERR_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) {
+    set_error("gemm_tc: operands must be 16-byte aligned");
+    return VRPX_ERR_ARG;
+  }
+  const int nw = a.NOUT * a.K;
+  if (nw > kMaxSplitWeights) {
+    set_error("gemm_tc: weight matrix too large for the split scratch (%d x %d)", a.NOUT, a.K);
+    return VRPX_ERR_ARG;
+  }
+  __half* w16 = split_scratch(stream);
+  if (!w16) return VRPX_ERR_CUDA;
+  k_split_w16<<<(nw + 255) / 256, 256, 0, stream>>>(a.W, w16, w16 + nw, nw);
+  VRPX_LAUNCH_CHECK();
+  CUtensorMap mx, mwh, mwl;
+  int rc;
+  if ((rc = make_map(&mx, a.X, a.R, a.K, false))) return rc;
+  if ((rc = make_map(&mwh, w16, a.NOUT, a.K, true))) return rc;
+  if ((rc = make_map(&mwl, w16 + nw, a.NOUT, a.K, true))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  // grid = (CTAs per column tile) x (column tiles): a multiple of nct, see the tile loop of the kernel
+  const int nct = a.NOUT / BN;
+  const int64_t nrt = (a.R + BM - 1) / BM;
+  int64_t per_ct = num_sms() / nct;
+  if (per_ct < 1) per_ct = 1;
+  if (per_ct > nrt) per_ct = nrt;
+  const int grid = (int)(per_ct * nct);
+  if (a.residual && a.gate) k_gemm_tc4<true, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else if (a.residual) k_gemm_tc4<true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else if (a.gate) k_gemm_tc4<false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else k_gemm_tc4<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+}  // namespace vrpx
+
+// Test hook: Y = epilogue(X · W^T) through any GEMM path (tests/test_gpu_gemm.py, tools/gemm_bench.py).
+extern "C" int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float* W, int32_t NOUT,
+                               const float* bias, int32_t relu, const float* residual, const float* scale,
+                               const float* shift, float* Y, int32_t path, void* stream) {
+  vrpx::GemmArgs g{X, R, K, W, NOUT, bias, relu, residual, scale, shift, Y};
+  return vrpx::gemm_dispatch(path, g, (cudaStream_t)stream);
+}
