@@ -3,6 +3,7 @@
 //
 // Dense contractions go through gemm_tc (tcgen05, f16 hi/lo split) or gemm_simt (fp32 FFMA cross-check);
 // the per-instance N x N attention (dh = 16) and the BatchNorm reductions are SIMT kernels here.
+#include "f16split.cuh"
 #include "gemm.cuh"
 
 namespace vrpx {
@@ -190,126 +191,142 @@ __global__ void __launch_bounds__(256) k_enc_attention(const float* __restrict__
 }
 
 // ---------------------------------------------------------------- per-instance self-attention on the tensor pipe
-// Same contract as k_enc_attention, computed with warp-level mma.sync.m16n8k8 TF32 and the 3-term split (~fp32):
-//   S = (Q/4) K^T  (16 queries x 8 keys per mma, 2 k-steps over dh = 16), row softmax in registers,
-//   O = P V        (the score accumulators are reused directly as A fragments: key order inside a key tile is
-//                   permuted, k-index t <-> key 2t, k-index t+4 <-> key 2t+1, and V is read with the same order).
-// One CTA per instance, one warp per head.  NTILES = ceil(N / 8) key tiles (compile-time bound on the registers).
-__device__ __forceinline__ void split_tf32_e(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32_e(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void mma3_e(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
-                                       uint32_t bl0, uint32_t bh1, uint32_t bl1) {
-  mma_tf32_e(c, al, bh0, bh1);
-  mma_tf32_e(c, ah, bl0, bl1);
-  mma_tf32_e(c, ah, bh0, bh1);
+// Same contract as k_enc_attention, computed with warp-level mma.sync.m16n8k16 on f16 hi/lo halves (f16split.cuh,
+// unscaled lo: Q/4, K, V and the probabilities are O(1)), ~fp32 accuracy:
+//   S = (Q/4) K^T   one k16 step covers the whole head dimension (16): 3 MMAs per 16 queries x 8 keys
+//   row softmax in registers
+//   O = P V         the score accumulators of two neighbouring key tiles ARE the A fragment of one k16 step over 16 keys
+// One CTA per instance, one warp per head.  K and V are split ONCE while they are staged in shared memory, in fragment
+// order, so the loops over query tiles read every B fragment with a single LDS.128 and do no conversions:
+//   Kf [head][key][lane t: {hi, lo} of dims (2t, 2t+1), {hi, lo} of dims (2t+8, 2t+9)]         16 B per (key, t)
+//   Vf [head][dim][k16 step jj][lane t: {hi, lo} of keys (16jj+2t, +1), {hi, lo} of keys (16jj+2t+8, +9)]
+//      dim stride padded by 4 chunks (the LDS.128 of a quarter warp — dims g in {2q, 2q+1}, t = 0..3 — is conflict free)
+//      and chunk position XOR 4 on every other group of 4 dims (so are the staging stores: dims d and d + 4 per quarter)
+// NJJ = ceil(N / 16) k16 steps over the keys (compile-time bound on the registers).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-constexpr int ATT_VLD = 20;  // padded V row stride (floats): B fragments (key 2t / 2t+1, dim g) hit 32 distinct banks
-
-template <int NTILES>
-__global__ void __launch_bounds__(256) k_enc_attention_mma(const float* __restrict__ qkv, float* __restrict__ att, int N) {
-  extern __shared__ __align__(16) float sm[];
-  const int NP = NTILES * 8;                       // keys padded to a multiple of 8
-  float* Ks = sm;                                  // [8 heads][NP][16]
-  float* Vs = sm + (size_t)NH * NP * 16;           // [8 heads][NP][ATT_VLD]
+template <int NJJ>
+__global__ void __launch_bounds__(256) k_enc_attention_f16(const float* __restrict__ qkv, float* __restrict__ att, int N) {
+  extern __shared__ __align__(16) uint4 smf[];
+  constexpr int NP = NJJ * 16;                     // keys padded to a multiple of 16
+  constexpr int VDS = 4 * (NJJ + (NJJ & 1)) + 4;   // chunks (16 B) per dim row of Vf
+  uint4* Kf = smf;                                 // [8][NP][4]
+  uint4* Vf = smf + NH * NP * 4;                   // [8][16][VDS]
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
   const float* base = qkv + b * N * 384;
-  for (int i = tid; i < NP * 64; i += 256) {       // 64 float4 per row of k|v
-    const int n = i >> 6, c4 = (i & 63) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < N) v = *reinterpret_cast<const float4*>(base + (int64_t)n * 384 + 128 + c4);
-    const int c = c4 & 127, hh = c >> 4, d = c & 15;
-    if (c4 < 128) *reinterpret_cast<float4*>(Ks + ((size_t)hh * NP + n) * 16 + d) = v;
-    else *reinterpret_cast<float4*>(Vs + ((size_t)hh * NP + n) * ATT_VLD + d) = v;
+  // K: thread -> (key n, head hh, lane slot t): dims 2t, 2t+1 and 2t+8, 2t+9 of the head
+  for (int i = tid; i < NP * 32; i += 256) {
+    const int t = i & 3, hh = (i >> 3) & 7, n = ((i >> 6) << 1) | ((i >> 2) & 1);   // a quarter warp stores keys n, n+1
+    float2 lo2 = make_float2(0.f, 0.f), hi2 = lo2;
+    if (n < N) {
+      const float* kp = base + (int64_t)n * 384 + 128 + hh * 16 + 2 * t;
+      lo2 = *reinterpret_cast<const float2*>(kp);
+      hi2 = *reinterpret_cast<const float2*>(kp + 8);
+    }
+    const uint2 p0 = split_f16x2_u(lo2.x, lo2.y), p1 = split_f16x2_u(hi2.x, hi2.y);
+    Kf[(hh * NP + n) * 4 + t] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+  }
+  // V: thread -> (k16 step jj, lane slot t, 4 consecutive dims c4..c4+3 of the 128): keys 16jj+2t, +1 and 16jj+2t+8, +9
+  for (int i = tid; i < NJJ * 4 * 32; i += 256) {
+    const int t = i & 3, c4 = ((i >> 2) & 31) * 4, jj = i >> 7;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int n = 16 * jj + 2 * t + (k & 1) + 8 * (k >> 1);
+      v[k] = (n < N) ? *reinterpret_cast<const float4*>(base + (int64_t)n * 384 + 256 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float e[4][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w},
+                           {v[2].x, v[2].y, v[2].z, v[2].w}, {v[3].x, v[3].y, v[3].z, v[3].w}};
+    const int hh = c4 >> 4, d0 = c4 & 15;
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      const uint2 p0 = split_f16x2_u(e[0][dd], e[1][dd]), p1 = split_f16x2_u(e[2][dd], e[3][dd]);
+      Vf[(hh * 16 + d0 + dd) * VDS + ((4 * jj + t) ^ (d0 & 4))] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+    }
   }
   __syncthreads();
   const int hh = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const float* Kh = Ks + (size_t)hh * NP * 16;
-  const float* Vh = Vs + (size_t)hh * NP * ATT_VLD;
+  const uint4* Kh = Kf + hh * NP * 4;
+  const uint4* Vh = Vf + hh * 16 * VDS;
   for (int q0 = 0; q0 < N; q0 += 16) {
     const int qa = q0 + g, qb = q0 + g + 8;
-    // A fragments of Q/4: thread t owns dims 4t..4t+3; k-step u: k-index t <-> dim 4t+2u, t+4 <-> dim 4t+2u+1
-    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-    if (qa < N) xa = *reinterpret_cast<const float4*>(base + (int64_t)qa * 384 + hh * 16 + 4 * t);
-    if (qb < N) xb = *reinterpret_cast<const float4*>(base + (int64_t)qb * 384 + hh * 16 + 4 * t);
-    const float ea[4] = {xa.x * 0.25f, xa.y * 0.25f, xa.z * 0.25f, xa.w * 0.25f};
-    const float eb[4] = {xb.x * 0.25f, xb.y * 0.25f, xb.z * 0.25f, xb.w * 0.25f};
-    uint32_t qh[2][4], ql[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      split_tf32_e(ea[2 * u], qh[u][0], ql[u][0]);
-      split_tf32_e(eb[2 * u], qh[u][1], ql[u][1]);
-      split_tf32_e(ea[2 * u + 1], qh[u][2], ql[u][2]);
-      split_tf32_e(eb[2 * u + 1], qh[u][3], ql[u][3]);
+    // A fragment of Q/4: a0 (row g, dims 2t, 2t+1), a1 (row g+8, same), a2 (row g, dims 2t+8, 2t+9), a3 (row g+8, same)
+    float2 xa0 = make_float2(0.f, 0.f), xa1 = xa0, xb0 = xa0, xb1 = xa0;
+    if (qa < N) {
+      const float* qp = base + (int64_t)qa * 384 + hh * 16 + 2 * t;
+      xa0 = *reinterpret_cast<const float2*>(qp);
+      xa1 = *reinterpret_cast<const float2*>(qp + 8);
     }
-    // ---- S = (Q/4) K^T
-    float sc[NTILES][4];
-#pragma unroll
-    for (int j = 0; j < NTILES; ++j) {
-      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-      const float4 kv = *reinterpret_cast<const float4*>(Kh + (8 * j + g) * 16 + 4 * t);   // key 8j+g, dims 4t..4t+3
-      const float ke[4] = {kv.x, kv.y, kv.z, kv.w};
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32_e(ke[2 * u], bh0, bl0);
-        split_tf32_e(ke[2 * u + 1], bh1, bl1);
-        mma3_e(sc[j], qh[u], ql[u], bh0, bl0, bh1, bl1);
-      }
+    if (qb < N) {
+      const float* qp = base + (int64_t)qb * 384 + hh * 16 + 2 * t;
+      xb0 = *reinterpret_cast<const float2*>(qp);
+      xb1 = *reinterpret_cast<const float2*>(qp + 8);
     }
-    // ---- row softmax: thread holds keys 8j + 2t, 8j + 2t + 1 of rows qa (sc[j][0..1]) and qb (sc[j][2..3])
+    uint32_t qh[4], ql[4];
+    {
+      // scores are kept in log2 units (Q scaled by log2(e) / sqrt(16)): the softmax needs one ex2 per element
+      constexpr float QS = 0.25f * 1.4426950408889634f;
+      const uint2 s0 = split_f16x2_u(xa0.x * QS, xa0.y * QS), s1 = split_f16x2_u(xb0.x * QS, xb0.y * QS);
+      const uint2 s2 = split_f16x2_u(xa1.x * QS, xa1.y * QS), s3 = split_f16x2_u(xb1.x * QS, xb1.y * QS);
+      qh[0] = s0.x; qh[1] = s1.x; qh[2] = s2.x; qh[3] = s3.x;
+      ql[0] = s0.y; ql[1] = s1.y; ql[2] = s2.y; ql[3] = s3.y;
+    }
+    // ---- S = (Q/4) K^T: C fragment of key tile j: [0], [1] = row g, keys 8j+2t, 8j+2t+1; [2], [3] = row g+8.
+    // Key tiles entirely beyond N are skipped (their probabilities stay 0); only the tile that straddles N is masked.
+    float sc[2 * NJJ][4];
     float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < NTILES; ++j) {
+    for (int j = 0; j < 2 * NJJ; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      if (8 * j < N) {
+        const uint4 kf = Kh[(8 * j + g) * 4 + t];   // B: (k = dims 2t.., n = key 8j+g)
+        mma3_f16(sc[j], qh, ql, kf.x, kf.z, kf.y, kf.w);
+        if (8 * j + 8 > N) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool ok = 8 * j + 2 * t + e < N;
-        if (!ok) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
-        ma = fmaxf(ma, sc[j][e]);
-        mb = fmaxf(mb, sc[j][2 + e]);
+          for (int e = 0; e < 2; ++e)
+            if (8 * j + 2 * t + e >= N) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
+        }
+        ma = fmaxf(ma, fmaxf(sc[j][0], sc[j][1]));
+        mb = fmaxf(mb, fmaxf(sc[j][2], sc[j][3]));
       }
     }
+    // ---- row softmax (thread holds keys 8j+2t, 8j+2t+1 of rows qa and qb)
     ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
     mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
     float sa = 0.f, sb = 0.f;
 #pragma unroll
-    for (int j = 0; j < NTILES; ++j) {
+    for (int j = 0; j < 2 * NJJ; ++j) {
+      if (8 * j < N) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        sc[j][e] = expf(sc[j][e] - ma);          // exp(-inf) = 0 for padded keys
-        sc[j][2 + e] = expf(sc[j][2 + e] - mb);
-        sa += sc[j][e];
-        sb += sc[j][2 + e];
+        for (int e = 0; e < 2; ++e) {
+          sc[j][e] = ex2_approx(sc[j][e] - ma);          // 2^(-inf) = 0 for the masked keys
+          sc[j][2 + e] = ex2_approx(sc[j][2 + e] - mb);
+          sa += sc[j][e];
+          sb += sc[j][2 + e];
+        }
       }
     }
     sa += __shfl_xor_sync(0xffffffffu, sa, 1); sa += __shfl_xor_sync(0xffffffffu, sa, 2);
     sb += __shfl_xor_sync(0xffffffffu, sb, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
-    // ---- O = P V  (A = P from the score registers; k-index t <-> key 8j+2t, t+4 <-> key 8j+2t+1)
+    // ---- O = P V: k16 step jj over keys 16jj..16jj+15; A = P from the score registers of key tiles 2jj, 2jj+1
     float o[2][4];
 #pragma unroll
     for (int d = 0; d < 2; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
 #pragma unroll
-    for (int j = 0; j < NTILES; ++j) {
-      uint32_t ph[4], pl[4];
-      split_tf32_e(sc[j][0], ph[0], pl[0]);   // (row g,   k = t)
-      split_tf32_e(sc[j][2], ph[1], pl[1]);   // (row g+8, k = t)
-      split_tf32_e(sc[j][1], ph[2], pl[2]);   // (row g,   k = t+4)
-      split_tf32_e(sc[j][3], ph[3], pl[3]);   // (row g+8, k = t+4)
-      const float* v0 = Vh + (8 * j + 2 * t) * ATT_VLD + g;
+    for (int jj = 0; jj < NJJ; ++jj) {
+      if (16 * jj >= N) continue;
+      const uint2 p0 = split_f16x2_u(sc[2 * jj][0], sc[2 * jj][1]), p1 = split_f16x2_u(sc[2 * jj][2], sc[2 * jj][3]);
+      const uint2 p2 = split_f16x2_u(sc[2 * jj + 1][0], sc[2 * jj + 1][1]), p3 = split_f16x2_u(sc[2 * jj + 1][2], sc[2 * jj + 1][3]);
+      const uint32_t ph[4] = {p0.x, p1.x, p2.x, p3.x}, pl[4] = {p0.y, p1.y, p2.y, p3.y};
 #pragma unroll
       for (int d = 0; d < 2; ++d) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32_e(v0[8 * d], bh0, bl0);               // (k = t,   n = dim 8d+g) = V[key 8j+2t][8d+g]
-        split_tf32_e(v0[ATT_VLD + 8 * d], bh1, bl1);     // (k = t+4, n = dim 8d+g) = V[key 8j+2t+1][8d+g]
-        mma3_e(o[d], ph, pl, bh0, bl0, bh1, bl1);
+        const uint4 vf = Vh[(8 * d + g) * VDS + ((4 * jj + t) ^ (g & 4))];   // B: (k = keys 16jj+2t.., n = dim 8d+g)
+        mma3_f16(o[d], ph, pl, vf.x, vf.z, vf.y, vf.w);
       }
     }
     const float ia = 1.0f / sa, ib = 1.0f / sb;
@@ -321,22 +338,21 @@ __global__ void __launch_bounds__(256) k_enc_attention_mma(const float* __restri
   }
 }
 
-static int launch_attention(const float* qkv, float* att, int64_t Bc, int N, cudaStream_t stream) {
-  const int nt = (N + 7) / 8;
-  const int NP = (nt <= 7 ? 7 : (nt <= 13 ? 13 : 16)) * 8;
-  const int smem = NH * NP * (16 + ATT_VLD) * (int)sizeof(float);
-  if (nt <= 7) {
-    VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_mma<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_enc_attention_mma<7><<<(unsigned)Bc, 256, smem, stream>>>(qkv, att, N);
-  } else if (nt <= 13) {
-    VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_mma<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_enc_attention_mma<13><<<(unsigned)Bc, 256, smem, stream>>>(qkv, att, N);
-  } else {
-    VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_enc_attention_mma<16><<<(unsigned)Bc, 256, smem, stream>>>(qkv, att, N);
-  }
+template <int NJJ>
+static int launch_attention_t(const float* qkv, float* att, int64_t Bc, int N, cudaStream_t stream) {
+  const int smem = (NH * NJJ * 16 * 4 + NH * 16 * (4 * (NJJ + (NJJ & 1)) + 4)) * (int)sizeof(uint4);
+  VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_f16<NJJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_enc_attention_f16<NJJ><<<(unsigned)Bc, 256, smem, stream>>>(qkv, att, N);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
+}
+
+static int launch_attention(const float* qkv, float* att, int64_t Bc, int N, cudaStream_t stream) {
+  const int njj = (N + 15) / 16;
+  if (njj <= 2) return launch_attention_t<2>(qkv, att, Bc, N, stream);
+  if (njj <= 4) return launch_attention_t<4>(qkv, att, Bc, N, stream);
+  if (njj <= 7) return launch_attention_t<7>(qkv, att, Bc, N, stream);
+  return launch_attention_t<8>(qkv, att, Bc, N, stream);
 }
 
 // ---------------------------------------------------------------- BatchNorm (graph_encoder.py:141-154)

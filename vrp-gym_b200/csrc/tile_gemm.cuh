@@ -2,9 +2,8 @@
 // recompute-based decoder backward (decoder_bwd.cu): tiles of 16 or 32 instances, 512 threads, tile GEMMs on the
 // warp-level tensor path (mma.sync TF32, 3-term split) with per-warp weight streams from L2 (cp.async rings).
 #pragma once
-#include <cuda_fp16.h>
-
 #include "env_rules.cuh"
+#include "f16split.cuh"
 
 namespace vrpx {
 
@@ -235,27 +234,8 @@ __device__ __forceinline__ void tile_gemm_tall_mma_sw(const float* __restrict__ 
 }
 
 // ================================================================ fp16-split tile GEMM (rollout GEMM-B)
-// Same ~fp32 accuracy as the 3xTF32 scheme at HALF the tensor-pipe time: mma.sync.m16n8k16 (f16 in, f32 accumulate)
-// issues at the rate of the TF32 m16n8k8 but covers twice the k range (tools/mma_bench3.cu: 958 vs 479 MAC/clk/SM).
-// Every fp32 operand x is carried as two halves  hi = f16(x),  lo = f16((x - hi) * 2^11)  — 22 significant bits like
-// the TF32 hi/lo pair (the 2^11 scale keeps lo in the normal f16 range whenever hi is).  hi·hi accumulates in one f32
-// accumulator, lo·hi + hi·lo in a second one that is folded in with 2^-11 at the end; lo·lo (2^-22) is dropped.
-// Operands must be below 65504 in magnitude (embeddings after BatchNorm and folded weights are O(10) at most).
-// Both operands are stored PRE-SPLIT as {hi2, lo2} = 8 bytes per pair of consecutive k, which is what one register of
-// the m16n8k16 fragments holds, so the k loop has no conversion arithmetic at all: one LDS.64 per fragment register pair.
-__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-constexpr float F16_LO_SCALE = 2048.0f;
-__device__ __forceinline__ uint2 split_f16x2(float x0, float x1) {   // {hi(x0) hi(x1), lo(x0) lo(x1)}
-  const __half2 h = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((x0 - hf.x) * F16_LO_SCALE, (x1 - hf.y) * F16_LO_SCALE);
-  return make_uint2(*reinterpret_cast<const uint32_t*>(&h), *reinterpret_cast<const uint32_t*>(&l));
-}
-
+// f16split.cuh, scaled-lo variant.  Both operands are stored PRE-SPLIT as {hi2, lo2} = 8 bytes per pair of consecutive k,
+// which is what one register of the m16n8k16 fragments holds, so the k loop has no conversion arithmetic at all.
 // A operand of the fp16-split tall GEMM: C16[16][C16_LD] uint2, element (m, kp) = split pair (k = 2kp, 2kp + 1) of row m,
 // stored at column kp ^ (((kp >> 7) & 3) << 2).  The XOR (by the head pair the k-pair belongs to) lets the producer
 // (rollout.cu, glimpse value pass: lanes of equal g and different t write different head pairs) store 16-byte chunks
