@@ -79,42 +79,52 @@ int gemm_simt(const GemmArgs& a, cudaStream_t stream) {
 // ---------------------------------------------------------------- embedding (graph_encoder.py:54, :110-132)
 // One thread per (row, 4 features of E).  Features are read from the env (f64 -> f32 cast, as
 // graph_tsp_agent.py:72 does) or from an explicit x[R][f] array.
-__global__ void k_embed(const vrpx_encoder_weights w, const double* __restrict__ xy,
-                        const double* __restrict__ demand, const float* __restrict__ x,
-                        const int32_t* __restrict__ depot, int64_t R, int N, float* __restrict__ h) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= R * (E / 4)) return;
-  int64_t r = idx / (E / 4);
-  int e0 = (int)(idx - r * (E / 4)) * 4;
-  float f[3] = {0.f, 0.f, 0.f};
-  if (x) {
-    for (int i = 0; i < w.f; ++i) f[i] = x[r * w.f + i];
-  } else {
-    f[0] = (float)xy[r * 2];
-    f[1] = (float)xy[r * 2 + 1];
-    if (w.f == 3) f[2] = (float)demand[r];
-  }
-  bool is_depot = false;
-  if (depot && w.depot_w) {
-    int64_t b = r / N;
-    is_depot = depot[b] == (int)(r - b * N);
-  }
-  float out[4];
+// One warp per row, lane = 4 output columns; the lane's slices of the (tiny) embedding weights live in registers and
+// the warp strides over the rows, so a row costs one broadcast load of its features, <= 12 FMAs and one 512-byte store.
+__global__ void __launch_bounds__(256) k_embed(const vrpx_encoder_weights w, const double* __restrict__ xy,
+                                               const double* __restrict__ demand, const float* __restrict__ x,
+                                               const int32_t* __restrict__ depot, int64_t R, int N, float* __restrict__ h) {
+  const int lane = threadIdx.x & 31, e0 = lane * 4, nf = w.f;
+  float nw[4][3], nb[4], dw[4][2], db[4];
+  const bool has_depot = depot && w.depot_w;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    int e = e0 + j;
-    float y;
-    if (is_depot) {
-      y = w.depot_b[e];
-      y = fmaf(f[0], w.depot_w[e * 2], y);
-      y = fmaf(f[1], w.depot_w[e * 2 + 1], y);
-    } else {
-      y = w.node_b[e];
-      for (int i = 0; i < w.f; ++i) y = fmaf(f[i], w.node_w[e * w.f + i], y);
-    }
-    out[j] = y;
+    nb[j] = w.node_b[e0 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nw[j][i] = (i < nf) ? w.node_w[(e0 + j) * nf + i] : 0.f;
+    db[j] = has_depot ? w.depot_b[e0 + j] : 0.f;
+    dw[j][0] = has_depot ? w.depot_w[(e0 + j) * 2] : 0.f;
+    dw[j][1] = has_depot ? w.depot_w[(e0 + j) * 2 + 1] : 0.f;
   }
-  *reinterpret_cast<float4*>(h + r * E + e0) = make_float4(out[0], out[1], out[2], out[3]);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < R; r += nwarps) {
+    float f[3] = {0.f, 0.f, 0.f};
+    if (x) {
+      for (int i = 0; i < nf; ++i) f[i] = x[r * nf + i];
+    } else {
+      const double2 p = *reinterpret_cast<const double2*>(xy + r * 2);
+      f[0] = (float)p.x;
+      f[1] = (float)p.y;
+      if (nf == 3) f[2] = (float)demand[r];
+    }
+    bool is_depot = false;
+    if (has_depot) {
+      const int64_t b = r / N;
+      is_depot = depot[b] == (int)(r - b * N);
+    }
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // same operation order as the one-thread-per-element version: bias, then the features in order
+      const float yd = fmaf(f[1], dw[j][1], fmaf(f[0], dw[j][0], db[j]));
+      float yn = nb[j];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (i < nf) yn = fmaf(f[i], nw[j][i], yn);
+      out[j] = is_depot ? yd : yn;
+    }
+    *reinterpret_cast<float4*>(h + r * E + e0) = make_float4(out[0], out[1], out[2], out[3]);
+  }
 }
 
 // ---------------------------------------------------------------- per-instance self-attention
@@ -198,8 +208,9 @@ __global__ void __launch_bounds__(256) k_enc_attention(const float* __restrict__
 //   O = P V         the score accumulators of two neighbouring key tiles ARE the A fragment of one k16 step over 16 keys
 // One CTA per instance, one warp per head.  K and V are split ONCE while they are staged in shared memory, in fragment
 // order, so the loops over query tiles read every B fragment with a single LDS.128 and do no conversions:
-//   Kf [head][key][lane t: {hi, lo} of dims (2t, 2t+1), {hi, lo} of dims (2t+8, 2t+9)]         16 B per (key, t)
-//   Vf [head][dim][k16 step jj][lane t: {hi, lo} of keys (16jj+2t, +1), {hi, lo} of keys (16jj+2t+8, +9)]
+//   Kf [head][key][lane t: hi(dims 2t, 2t+1), hi(dims 2t+8, 2t+9), lo(..), lo(..)]              16 B per (key, t)
+//   Vf [head][dim][k16 step jj][lane t: hi(keys 16jj+2t, +1), hi(keys 16jj+2t+8, +9), lo(..), lo(..)]
+//      (hi pair and lo pair adjacent: each is the two-register B operand of one HMMA, no register moves)
 //      dim stride padded by 4 chunks (the LDS.128 of a quarter warp — dims g in {2q, 2q+1}, t = 0..3 — is conflict free)
 //      and chunk position XOR 4 on every other group of 4 dims (so are the staging stores: dims d and d + 4 per quarter)
 // NJJ = ceil(N / 16) k16 steps over the keys (compile-time bound on the registers).
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(256) k_enc_attention_f16(const float* __restri
       hi2 = *reinterpret_cast<const float2*>(kp + 8);
     }
     const uint2 p0 = split_f16x2_u(lo2.x, lo2.y), p1 = split_f16x2_u(hi2.x, hi2.y);
-    Kf[(hh * NP + n) * 4 + t] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+    Kf[(hh * NP + n) * 4 + t] = make_uint4(p0.x, p1.x, p0.y, p1.y);
   }
   // V: thread -> (k16 step jj, lane slot t, 4 consecutive dims c4..c4+3 of the 128): keys 16jj+2t, +1 and 16jj+2t+8, +9
   for (int i = tid; i < NJJ * 4 * 32; i += 256) {
@@ -246,27 +257,31 @@ __global__ void __launch_bounds__(256) k_enc_attention_f16(const float* __restri
 #pragma unroll
     for (int dd = 0; dd < 4; ++dd) {
       const uint2 p0 = split_f16x2_u(e[0][dd], e[1][dd]), p1 = split_f16x2_u(e[2][dd], e[3][dd]);
-      Vf[(hh * 16 + d0 + dd) * VDS + ((4 * jj + t) ^ (d0 & 4))] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+      Vf[(hh * 16 + d0 + dd) * VDS + ((4 * jj + t) ^ (d0 & 4))] = make_uint4(p0.x, p1.x, p0.y, p1.y);
     }
   }
   __syncthreads();
   const int hh = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const uint4* Kh = Kf + hh * NP * 4;
   const uint4* Vh = Vf + hh * 16 * VDS;
+  // A fragment of Q/4: a0 (row g, dims 2t, 2t+1), a1 (row g+8, same), a2 (row g, dims 2t+8, 2t+9), a3 (row g+8, same);
+  // the rows of the NEXT query tile are fetched while the current one is processed
+  auto load_q = [&](int q, float2& x0, float2& x1) {
+    x0 = x1 = make_float2(0.f, 0.f);
+    if (q < N) {
+      const float* qp = base + (int64_t)q * 384 + hh * 16 + 2 * t;
+      x0 = *reinterpret_cast<const float2*>(qp);
+      x1 = *reinterpret_cast<const float2*>(qp + 8);
+    }
+  };
+  float2 na0, na1, nb0, nb1;
+  load_q(g, na0, na1);
+  load_q(g + 8, nb0, nb1);
   for (int q0 = 0; q0 < N; q0 += 16) {
     const int qa = q0 + g, qb = q0 + g + 8;
-    // A fragment of Q/4: a0 (row g, dims 2t, 2t+1), a1 (row g+8, same), a2 (row g, dims 2t+8, 2t+9), a3 (row g+8, same)
-    float2 xa0 = make_float2(0.f, 0.f), xa1 = xa0, xb0 = xa0, xb1 = xa0;
-    if (qa < N) {
-      const float* qp = base + (int64_t)qa * 384 + hh * 16 + 2 * t;
-      xa0 = *reinterpret_cast<const float2*>(qp);
-      xa1 = *reinterpret_cast<const float2*>(qp + 8);
-    }
-    if (qb < N) {
-      const float* qp = base + (int64_t)qb * 384 + hh * 16 + 2 * t;
-      xb0 = *reinterpret_cast<const float2*>(qp);
-      xb1 = *reinterpret_cast<const float2*>(qp + 8);
-    }
+    const float2 xa0 = na0, xa1 = na1, xb0 = nb0, xb1 = nb1;
+    load_q(qa + 16, na0, na1);
+    load_q(qb + 16, nb0, nb1);
     uint32_t qh[4], ql[4];
     {
       // scores are kept in log2 units (Q scaled by log2(e) / sqrt(16)): the softmax needs one ex2 per element
@@ -285,7 +300,7 @@ __global__ void __launch_bounds__(256) k_enc_attention_f16(const float* __restri
       sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
       if (8 * j < N) {
         const uint4 kf = Kh[(8 * j + g) * 4 + t];   // B: (k = dims 2t.., n = key 8j+g)
-        mma3_f16(sc[j], qh, ql, kf.x, kf.z, kf.y, kf.w);
+        mma3_f16(sc[j], qh, ql, kf.x, kf.y, kf.z, kf.w);
         if (8 * j + 8 > N) {
 #pragma unroll
           for (int e = 0; e < 2; ++e)
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(256) k_enc_attention_f16(const float* __restri
 #pragma unroll
       for (int d = 0; d < 2; ++d) {
         const uint4 vf = Vh[(8 * d + g) * VDS + ((4 * jj + t) ^ (g & 4))];   // B: (k = keys 16jj+2t.., n = dim 8d+g)
-        mma3_f16(o[d], ph, pl, vf.x, vf.z, vf.y, vf.w);
+        mma3_f16(o[d], ph, pl, vf.x, vf.y, vf.z, vf.w);
       }
     }
     const float ia = 1.0f / sa, ib = 1.0f / sb;
@@ -488,8 +503,8 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
     float* sv_stats = saved ? saved + R * kSavedRowFloats : nullptr;
     if (saved) hc = saved;            // H[0]: the embedding is the input of layer 0
     {
-      int64_t n = R * (E / 4);
-      k_embed<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      const int64_t want = (R + 7) / 8, cap = (int64_t)num_sms() * 8;   // 8 warps (rows in flight) per CTA
+      k_embed<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(
           *w, (!x && env) ? env->xy + b0 * N * 2 : nullptr,
           (!x && env && env->demand) ? env->demand + b0 * N : nullptr, x ? x + b0 * N * w->f : nullptr,
           depot ? depot + b0 : nullptr, R, N, hc);

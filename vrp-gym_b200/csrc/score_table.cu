@@ -6,7 +6,7 @@
 // per head (A_l,head = W_k,head^T · W_l,head / sqrt(48), the reference's own query/key projections).  So once per
 // episode:
 //     QK = h · qk_w^T                      (B·N) x 768 on tcgen05 (gemm_tc): q'[b,l] | k'[b,n], 8 heads x 48
-//     S1[b][l][head][n] = q'[b,l,head] · k'[b,n,head]        this kernel, mma.sync TF32 3-term split
+//     S1[b][l][head][n] = q'[b,l,head] · k'[b,n,head]        this kernel, mma.sync on f16 hi/lo halves (~fp32)
 // and the decode steps read the 8·N scores of row (b, last) instead of running the 128 -> 1024 tile GEMM and the
 // 8·N·128 score pass every step.  Algorithmic cost: the table holds B·N·8·N floats (5.2 GB at TSP-50, B = 65536).
 #include "gemm.cuh"
@@ -18,23 +18,30 @@ constexpr int DQK = 48;            // decoder head dim (384 / 8)
 constexpr int QKW = 2 * NH * DQK;  // 768 columns of QK
 
 // One CTA per instance and half of the heads (grid.y = 2), one warp per head: 4-warp CTAs keep the shared-memory
-// footprint at 43 KB (N = 50) so that five CTAs share an SM and cover the global-load latency.  The warp stages k'[b, :, head] (N x 48, unpadded: LDS.128 of the B
-// fragments is conflict free at a 48-float pitch) in shared memory, streams q' rows from global memory as A fragments
-// and writes S1 rows.  The K axis (48) is permuted so that every thread loads whole float4 chunks: chunk c (0..2) of
-// thread t covers dims 16c + 4t + {0,1,2,3}; k-step 2c + u uses mma k-index t <-> dim 16c+4t+2u and t+4 <-> 16c+4t+2u+1.
+// footprint at 43 KB (N = 50) so that five CTAs share an SM and cover the global-load latency.  Contractions run on
+// mma.sync.m16n8k16 with f16 hi/lo halves (f16split.cuh, unscaled lo: q' and k' are O(1) projections), ~fp32 accuracy.
+// The warp splits k'[b, :, head] (N x 48) ONCE into fragment order in shared memory —
+//   Ks [key][k16 step c][lane t: hi(dims 16c+2t, +1), hi(dims 16c+2t+8, +9), lo(..), lo(..)]    16 B per (key, c, t)
+// (one conflict-free LDS.128 per B fragment, hi / lo pairs adjacent as the two-register HMMA operand) — then streams q'
+// rows from global memory as A fragments and writes S1 rows.
 template <int NT8>
 __global__ void __launch_bounds__(128) k_score_table(const float* __restrict__ qk, float* __restrict__ s1, int N) {
-  extern __shared__ __align__(16) float ks_all[];
+  extern __shared__ __align__(16) uint4 ks_all[];
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int warp = blockIdx.y * 4 + (threadIdx.x >> 5);   // = head
   const int64_t b = blockIdx.x;
-  float* Ks = ks_all + (threadIdx.x >> 5) * (NT8 * 8 * DQK);
+  uint4* Ks = ks_all + (threadIdx.x >> 5) * (NT8 * 8 * 12);
   const float* qkb = qk + b * N * QKW;
-  for (int idx = lane; idx < NT8 * 8 * (DQK / 4); idx += 32) {
-    const int n = idx / (DQK / 4), c4 = idx % (DQK / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < N) v = __ldg(reinterpret_cast<const float4*>(qkb + (size_t)n * QKW + NH * DQK + warp * DQK) + c4);
-    *reinterpret_cast<float4*>(Ks + n * DQK + c4 * 4) = v;
+  for (int idx = lane; idx < NT8 * 8 * 12; idx += 32) {
+    const int n = idx / 12, c = (idx >> 2) % 3, tt = idx & 3;
+    float2 x0 = make_float2(0.f, 0.f), x1 = x0;
+    if (n < N) {
+      const float* kp = qkb + (size_t)n * QKW + NH * DQK + warp * DQK + 16 * c + 2 * tt;
+      x0 = __ldg(reinterpret_cast<const float2*>(kp));
+      x1 = __ldg(reinterpret_cast<const float2*>(kp + 8));
+    }
+    const uint2 p0 = split_f16x2_u(x0.x, x0.y), p1 = split_f16x2_u(x1.x, x1.y);
+    Ks[idx] = make_uint4(p0.x, p1.x, p0.y, p1.y);
   }
   __syncwarp();
   const bool vec_ok = (N & 1) == 0;
@@ -45,39 +52,26 @@ __global__ void __launch_bounds__(128) k_score_table(const float* __restrict__ q
     for (int j = 0; j < NT8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-    float4 qa[3], qb[3];
+    // A fragments of the three k16 steps: a0 (row la, dims 16c+2t, +1), a1 (row lb, same), a2 (row la, dims 16c+2t+8, +9), a3
+    float2 qa[3][2], qb[3][2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      qa[c] = (la < N) ? __ldg(reinterpret_cast<const float4*>(qkb + (size_t)la * QKW + warp * DQK + 16 * c) + t)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      qb[c] = (lb < N) ? __ldg(reinterpret_cast<const float4*>(qkb + (size_t)lb * QKW + warp * DQK + 16 * c) + t)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float ae[4] = {qa[c].x, qa[c].y, qa[c].z, qa[c].w};
-      const float be[4] = {qb[c].x, qb[c].y, qb[c].z, qb[c].w};
-      uint32_t ah[2][4], al[2][4];
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        split_tf32(ae[2 * u], ah[u][0], al[u][0]);       // (row g,   k = t)
-        split_tf32(be[2 * u], ah[u][1], al[u][1]);       // (row g+8, k = t)
-        split_tf32(ae[2 * u + 1], ah[u][2], al[u][2]);   // (row g,   k = t+4)
-        split_tf32(be[2 * u + 1], ah[u][3], al[u][3]);   // (row g+8, k = t+4)
+        qa[c][u] = (la < N) ? __ldg(reinterpret_cast<const float2*>(qkb + (size_t)la * QKW + warp * DQK + 16 * c + 2 * t + 8 * u))
+                            : make_float2(0.f, 0.f);
+        qb[c][u] = (lb < N) ? __ldg(reinterpret_cast<const float2*>(qkb + (size_t)lb * QKW + warp * DQK + 16 * c + 2 * t + 8 * u))
+                            : make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < NT8; ++j) {
-        const float4 kv = *reinterpret_cast<const float4*>(Ks + (8 * j + g) * DQK + 16 * c + 4 * t);
-        const float ke[4] = {kv.x, kv.y, kv.z, kv.w};
+    for (int c = 0; c < 3; ++c) {
+      const uint2 s0 = split_f16x2_u(qa[c][0].x, qa[c][0].y), s1_ = split_f16x2_u(qb[c][0].x, qb[c][0].y);
+      const uint2 s2 = split_f16x2_u(qa[c][1].x, qa[c][1].y), s3 = split_f16x2_u(qb[c][1].x, qb[c][1].y);
+      const uint32_t ah[4] = {s0.x, s1_.x, s2.x, s3.x}, al[4] = {s0.y, s1_.y, s2.y, s3.y};
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          uint32_t bh0, bl0, bh1, bl1;
-          split_tf32(ke[2 * u], bh0, bl0);       // (k = t,   n = g)
-          split_tf32(ke[2 * u + 1], bh1, bl1);   // (k = t+4, n = g)
-          mma_tf32_16x8x8(acc[j], al[u], bh0, bh1);
-          mma_tf32_16x8x8(acc[j], ah[u], bl0, bl1);
-          mma_tf32_16x8x8(acc[j], ah[u], bh0, bh1);
-        }
+      for (int j = 0; j < NT8; ++j) {
+        const uint4 kf = Ks[((8 * j + g) * 3 + c) * 4 + t];   // B: (k = dims 16c+2t.., n = key 8j+g)
+        mma3_f16(acc[j], ah, al, kf.x, kf.y, kf.z, kf.w);
       }
     }
     // C fragment: acc[j][0..1] = (l = la, n = 8j + 2t, +1), acc[j][2..3] = (l = lb, ...)
@@ -107,7 +101,7 @@ __global__ void __launch_bounds__(128) k_score_table(const float* __restrict__ q
 
 template <int NT8>
 static int launch_score_table(const float* qk, float* s1, int64_t nb, int N, cudaStream_t stream) {
-  const int smem = (NH / 2) * NT8 * 8 * DQK * (int)sizeof(float);
+  const int smem = (NH / 2) * NT8 * 8 * 12 * (int)sizeof(uint4);
   VRPX_CUDA(cudaFuncSetAttribute(k_score_table<NT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   k_score_table<NT8><<<dim3((unsigned)nb, 2), 128, smem, stream>>>(qk, s1, N);
   VRPX_LAUNCH_CHECK();
