@@ -257,7 +257,7 @@ typedef struct vrpx_decoder_grads {
 
 VRPX_API int64_t vrpx_decoder_backward_workspace_bytes(int64_t B, int32_t N);
 
-/* Backward of vrpx_rollout for one episode.  `trace` and `qg` (the rollout workspace's Q~g table = ws + 4096 bytes)
+/* Backward of vrpx_rollout for one episode.  `trace` and `qg` (the rollout workspace's Q~g table = ws + vrpx_rollout_workspace_qg_offset() bytes)
  * come from the forward call that produced `tape`; T = number of executed steps; wts [B] f32. */
 VRPX_API int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, const vrpx_decoder_bwd_weights* wb,
                                    const float* h, const uint8_t* tape, int32_t T, int64_t coupling,

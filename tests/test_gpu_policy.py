@@ -239,3 +239,60 @@ def test_score_table_mode_matches_classic(kind, N, B):
     assert np.array_equal(fin, np.isfinite(got))
     assert _rel(got[fin], ref[fin]) < 1e-5
     assert _rel(loss1.cpu().numpy(), loss0.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("kind,N,B,greedy", [("irp", 40, 4096, False), ("tsp", 50, 65536, True), ("vrp", 100, 131072, True)],
+                         ids=["C3_irp40_b4096_sampled", "C4_tsp50_b65536", "C5_vrp100_b131072_per_gpu"])
+def test_baseline_config_sizes_properties(kind, N, B, greedy):
+    """BASELINE.json configs[2..4] at their full (per-GPU) sizes, whole-batch mask coupling like the bench, checked through
+    size-independent properties of the domain (the oracle cannot run these sizes in seconds):
+    * every customer is visited exactly once, nothing is visited at a masked position, TSP tours take N-1 steps;
+    * the f32 cost of every instance equals its tour length recomputed on the host from the action tape;
+    * IRP: the vehicle load between two depot visits never exceeds 1 (the demand of every served customer fitted);
+    * sampled rollouts: finite, non-positive log-probabilities."""
+    Env, Agent = _cls(kind)
+    env = Env(N, B, 0, seed=11, instance_rng="philox")
+    agent = Agent(seed=11)
+    agent.model.eval()
+    with torch.no_grad():
+        if greedy:
+            loss = agent.evaluate(env)
+            logp = None
+        else:
+            torch.manual_seed(5)
+            loss, logp = agent.model(env, rollout=False)
+    out = agent.model.last_rollout
+    tape = out["tape"].cpu().numpy()
+    T = tape.shape[0]
+    s = env.sampler
+    xy, depot, demand = s.get_graph_positions(), s.get_depots()[:, 0], s.get_demands()[:, :, 0]
+    assert tape.max() < N
+    if kind == "tsp":
+        assert T == N - 1
+    else:
+        assert N - 1 <= T <= 2 * (N - 1)
+    ar = np.arange(B)
+    counts = np.zeros((B, N), dtype=np.int32)
+    for t in range(T):
+        np.add.at(counts, (ar, tape[t]), 1)
+    cust = np.ones((B, N), dtype=bool)
+    cust[ar, depot] = False
+    assert np.all(counts[cust] == 1), "a customer was skipped or visited twice"
+    if kind == "tsp":
+        assert np.all(counts[~cust] == 0), "a TSP tour returned to its depot"
+    cur = depot.copy()
+    acc = np.zeros(B, dtype=np.float32)
+    load = np.ones(B)
+    for t in range(T):
+        a = tape[t].astype(np.int64)
+        d = xy[ar, cur] - xy[ar, a]
+        acc = acc + np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2).astype(np.float32)
+        if kind == "irp":
+            load = load - demand[ar, a]
+            assert load.min() > -1e-12, "an IRP vehicle served a customer it had no load for"
+            load[a == depot] = 1.0
+        cur = a
+    assert np.allclose(-loss.cpu().numpy(), acc, rtol=2e-6, atol=2e-6)
+    if logp is not None:
+        lp = logp.cpu().numpy()
+        assert np.isfinite(lp).all() and (lp <= 0).all()
