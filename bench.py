@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=4096, help="instances in the bounded CPU sample")
     ap.add_argument("--gemm-path", type=int, default=0, help="0 tcgen05 f16-split (production), 1 fp32 SIMT, 2 tcgen05 3xTF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-split", action="store_true",
+                    help="keep every decode step inside the persistent kernel (A/B against the split-step launches)")
     ap.add_argument("--seed", type=int, default=69)
     ap.add_argument("--mode", default="rollout", choices=["rollout", "train"],
                     help="rollout: greedy evaluate (headline); train: one REINFORCE step (sampled rollout + sampled "
@@ -272,7 +274,9 @@ def main():
     e0.record()
     total_inst_steps = 0
     kernel_ms = []
-    vrpx.lib().vrpx_debug_rollout_timing(1)  # CUDA events around the persistent kernel alone, on its launch stream
+    if a.no_split:
+        vrpx.lib().vrpx_debug_rollout_split(0)
+    vrpx.lib().vrpx_debug_rollout_timing(1)  # CUDA events around the decode launches alone, on their launch stream
     for i in range(a.steps):
         out = one_step(per_step_events[i])
         total_inst_steps += out["steps"] * B  # includes the .item() sync on the step count

@@ -230,11 +230,14 @@ VRPX_API int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, co
 /* Measurement hooks (bench.py, tools/): not part of the reference surface.
  *   vrpx_debug_rollout_profile  device buffer of 8 x int64 that accumulates per-phase cycles of thread 0 of every CTA
  *                               of the rollout kernel (NULL disables)
- *   vrpx_debug_rollout_timing   when enabled, vrpx_rollout brackets the persistent kernel launch (alone, without the
+ *   vrpx_debug_rollout_timing   when enabled, vrpx_rollout brackets the decode launches (persistent kernel + step kernels, without the
  *                               score-table prologue kernels) with CUDA events on the launch stream
  *   vrpx_debug_rollout_kernel_ms  waits for the last bracketed launch and returns its duration (-1 if none) */
 VRPX_API void vrpx_debug_rollout_profile(long long* dev_counters);
 VRPX_API void vrpx_debug_rollout_timing(int32_t enable);
+/* Table mode runs the decode steps t >= 2 as three launches per step over the whole batch (default, enable = 1) or
+ * keeps every step inside the persistent kernel (enable = 0; cross-check and A/B measurements). */
+VRPX_API void vrpx_debug_rollout_split(int32_t enable);
 VRPX_API float vrpx_debug_rollout_kernel_ms(void);
 
 /* ---------------------------------------------------------------- REINFORCE backward (decoder part)

@@ -15,38 +15,10 @@
 //
 // Step-invariant work the reference repeats every step (K/V/kp projections, graph mean) is folded into
 // host-packed weights (vrpx/packing.py) and the per-episode Q~g table built in the prologue.
-#include "tile_gemm.cuh"
+#include "rollout.cuh"
 
 namespace vrpx {
 
-struct RolloutParams {
-  vrpx_env env;
-  vrpx_decoder_weights w;
-  const float* h;
-  int mode;
-  long long G;
-  unsigned long long seed, offset;
-  uint8_t* tape;
-  int t0;
-  int Tmax;
-  float* logp;
-  float* cost;
-  int* steps;
-  float* logits;
-  float* qg;          // [B][1024]
-  float* qg0;         // optional copy of Q~g before the `first` fold (backward)
-  uint32_t* mask_hist;  // optional [Tmax][B][4] decoder-visible mask before each step (backward)
-  float* load_hist;   // optional [Tmax][B] f32 vehicle load before each step (backward)
-  unsigned* bar;      // grid barrier counter
-  int* notdone;       // [Tmax + 1]
-  long long* prof;    // optional [8] cycle counters per phase (debug, vrpx_debug_rollout_profile)
-  // table mode (score_table.cu): per-episode glimpse score tables, all NULL in the classic mode
-  const float* s1;    // [B][N][8][N]  (A_l h[b,l])_head · h[b,n], built before the launch
-  float* s0;          // [B][8][N]     Q~g[b]_head · h[b,n], built at step 1 (after the `first` fold)
-  float* sl;          // [B][8][N]     IRP: a_load_head · h[b,n]
-  const uint2* m16;   // [512][128] m_t pre-split for the fp16 tensor path (k_split_m16, tile_gemm.cuh)
-  int tb_segs;        // table rows staged in shared memory per instance: 0 none, 1 = S1, 2 = S1 + S0, 3 = S1 + S0 + SL
-};
 
 int64_t score_table_slice(int64_t B);
 int build_score_table(const float* h, const float* qk_w, int64_t B, int N, float* qk_buf, float* s1, cudaStream_t stream);
@@ -626,6 +598,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
 }
 
 static long long* g_rollout_prof = nullptr;
+static int g_split_steps = 1;                        // vrpx_debug_rollout_split
 static int g_time_kernel = 0;                        // vrpx_debug_rollout_timing
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static bool g_ev_valid = false;
@@ -641,6 +614,8 @@ extern "C" {
 
 /* Debug hook: device buffer of 8 x int64 that accumulates per-phase cycles of thread 0 of every CTA (NULL disables). */
 void vrpx_debug_rollout_profile(long long* dev_counters) { g_rollout_prof = dev_counters; }
+
+void vrpx_debug_rollout_split(int32_t enable) { g_split_steps = enable; }
 
 void vrpx_debug_rollout_timing(int32_t enable) {
   g_time_kernel = enable;
@@ -661,10 +636,10 @@ int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N) {
 
 int64_t vrpx_rollout_workspace_qg_offset(void) { return kRolloutHdr; }
 
-// table-mode workspace: header | Q~g | S0 | SL (IRP) | S1 | QK slice, every segment 256-byte aligned
+// table-mode workspace: header | Q~g | S0 | SL (IRP) | S1 | QK slice | c | q^ | m_t^T, every segment 256-byte aligned
 namespace {
 struct TableLayout {
-  int64_t s0, sl, s1, qk, total;
+  int64_t s0, sl, s1, qk, cbuf, qhat, mnt, total;
 };
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 TableLayout table_layout(int kind, int64_t B, int N) {
@@ -674,7 +649,11 @@ TableLayout table_layout(int kind, int64_t B, int N) {
   L.sl = align256(L.s0 + B * NH * N * f);
   L.s1 = (kind == VRPX_IRP) ? align256(L.sl + B * NH * N * f) : L.sl;
   L.qk = align256(L.s1 + B * N * NH * N * f);
-  L.total = align256(L.qk + score_table_slice(B) * N * 768 * f);
+  // split-step mode (rollout_steps.cu): glimpse vectors, folded queries, transposed m_t
+  L.cbuf = align256(L.qk + score_table_slice(B) * N * 768 * f);
+  L.qhat = align256(L.cbuf + B * QW * f);
+  L.mnt = align256(L.qhat + B * E * f);
+  L.total = align256(L.mnt + (int64_t)QW * E * f);
   return L;
 }
 }  // namespace
@@ -725,6 +704,8 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   p.m16 = reinterpret_cast<const uint2*>(reinterpret_cast<char*>(ws) + kRolloutSmall);
   p.s1 = nullptr;
   p.s0 = p.sl = nullptr;
+  p.cbuf = p.qhat = nullptr;
+  float* m_nt = nullptr;
   // table mode: whole-episode call with the large workspace and the rank-48 factors
   if (w->qk_w && t_begin == 0 && Tmax >= 3) {
     const TableLayout L = table_layout(env->kind, env->B, env->N);
@@ -736,7 +717,18 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
       p.s1 = s1;
       p.s0 = reinterpret_cast<float*>(base + L.s0);
       p.sl = reinterpret_cast<float*>(base + L.sl);
+      p.cbuf = reinterpret_cast<float*>(base + L.cbuf);
+      p.qhat = reinterpret_cast<float*>(base + L.qhat);
+      m_nt = reinterpret_cast<float*>(base + L.mnt);
     }
+  }
+  // Split-step mode: the persistent kernel runs steps 0 and 1 (classic phases, they build Q~g and S0), every later step
+  // is three launches over the whole batch (rollout_steps.cu)
+  const bool split = p.s1 != nullptr && g_split_steps;
+  if (split) {
+    int rc = prepare_split_weights(w->m_t, m_nt, stream);
+    if (rc) return rc;
+    p.Tmax = 2;
   }
   // shared-memory staging of the table rows: as many segments as fit beside the GEMM buffers
   p.tb_segs = 0;
@@ -766,6 +758,11 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   }
   VRPX_CUDA(cudaLaunchCooperativeKernel((void*)k_rollout, dim3(grid), dim3(NT), args, smem_total, stream));
   count_launch();
+  if (split) {
+    p.Tmax = Tmax;
+    int rc = run_split_steps(p, t_begin + 2, m_nt, stream);
+    if (rc) return rc;
+  }
   if (g_time_kernel) {
     VRPX_CUDA(cudaEventRecord(g_ev1, stream));
     g_ev_valid = true;

@@ -1,0 +1,45 @@
+// rollout.cuh — parameter block shared by the persistent rollout kernel (rollout.cu) and the split-step kernels
+// (rollout_steps.cu).
+#pragma once
+#include "tile_gemm.cuh"
+
+namespace vrpx {
+
+struct RolloutParams {
+  vrpx_env env;
+  vrpx_decoder_weights w;
+  const float* h;
+  int mode;
+  long long G;
+  unsigned long long seed, offset;
+  uint8_t* tape;
+  int t0;
+  int Tmax;
+  float* logp;
+  float* cost;
+  int* steps;
+  float* logits;
+  float* qg;          // [B][1024]
+  float* qg0;         // optional copy of Q~g before the `first` fold (backward)
+  uint32_t* mask_hist;  // optional [Tmax][B][4] decoder-visible mask before each step (backward)
+  float* load_hist;   // optional [Tmax][B] f32 vehicle load before each step (backward)
+  unsigned* bar;      // grid barrier counter
+  int* notdone;       // [Tmax + 1]
+  long long* prof;    // optional [8] cycle counters per phase (debug, vrpx_debug_rollout_profile)
+  // table mode (score_table.cu): per-episode glimpse score tables, all NULL in the classic mode
+  const float* s1;    // [B][N][8][N]  (A_l h[b,l])_head · h[b,n], built before the launch
+  float* s0;          // [B][8][N]     Q~g[b]_head · h[b,n], built at step 1 (after the `first` fold)
+  float* sl;          // [B][8][N]     IRP: a_load_head · h[b,n]
+  const uint2* m16;   // [512][128] m_t pre-split for the fp16 tensor path (k_split_m16, tile_gemm.cuh)
+  // split-step mode (rollout_steps.cu): glimpse vectors c [B][1024] and folded queries q^ [B][128] in global memory
+  float* cbuf;
+  float* qhat;
+  int tb_segs;        // table rows staged in shared memory per instance: 0 none, 1 = S1, 2 = S1 + S0, 3 = S1 + S0 + SL
+};
+
+// rollout_steps.cu: decode steps [t_first, t0 + Tmax) as three launches per step (glimpse, batched GEMM-B, pointer) and
+// the final step count; m_nt = m_t transposed ([128][1024], built by prepare_split_weights).
+int prepare_split_weights(const float* m_t, float* m_nt, cudaStream_t stream);
+int run_split_steps(const RolloutParams& p, int t_first, const float* m_nt, cudaStream_t stream);
+
+}  // namespace vrpx

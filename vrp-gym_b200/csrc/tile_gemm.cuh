@@ -70,6 +70,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // glimpse-mask source row for attention row (b, hh): mask.repeat(H,1) indexing (graph_decoder.py:93)
 __device__ __forceinline__ int64_t quirk_row(int64_t b, int hh, long long G) {
   if (G <= 0) return b;
+  if (G < (1ll << 28) && b < (1ll << 31)) {   // 32-bit arithmetic (every per-GPU batch): two cheap divisions per call
+    const uint32_t g = (uint32_t)G, bb = (uint32_t)b, g0 = (bb / g) * g;
+    return (int64_t)(g0 + ((bb - g0) * NH + (uint32_t)hh) % g);
+  }
   int64_t g0 = (b / G) * G;
   return g0 + (((b - g0) * NH + hh) % G);
 }

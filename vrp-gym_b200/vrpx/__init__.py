@@ -133,6 +133,8 @@ def lib():
     L.vrpx_rollout_table_workspace_bytes.restype = i64
     L.vrpx_debug_rollout_profile.argtypes = [C.c_void_p]
     L.vrpx_debug_rollout_profile.restype = None
+    L.vrpx_debug_rollout_split.argtypes = [i32]
+    L.vrpx_debug_rollout_split.restype = None
     L.vrpx_debug_rollout_timing.argtypes = [i32]
     L.vrpx_debug_rollout_timing.restype = None
     L.vrpx_debug_rollout_kernel_ms.argtypes = []
