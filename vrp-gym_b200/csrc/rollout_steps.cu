@@ -20,7 +20,18 @@
 
 namespace vrpx {
 
-constexpr int SW = 8;   // warps (= instances) per CTA of the step kernels
+constexpr int SW = 8;   // warps (= instances) per CTA of the pointer kernel
+// glimpse kernel: up to 10 warps per CTA, two CTAs per SM.  Every warp streams its instance's embeddings through a
+// private cp.async ring of GNS slices of 8 node rows (rows padded to 544 B: the LDS.128 fragment reads are conflict free),
+// so the loads in flight cost no registers; the P[n][8] slot behind the ring is sized by N.  Measured at C4: the kernel is
+// bound by dependent-instruction latency, i.e. by the number of resident warps (11 warps: 451 us, as much as the
+// register-staged version at 15 warps with its exposed load latency).
+constexpr int GW_MAX = 10, GNS = 2;
+constexpr int G_ROW = 544;                          // bytes per staged node row (512 + 32)
+constexpr int G_SLICE = 8 * G_ROW;                  // 4352 B
+constexpr int G_CTA_SMEM = 113 * 1024;              // two CTAs per SM
+static_assert(GNS * G_SLICE >= QW * 4, "c[1024] is staged in the ring");
+__host__ __device__ inline int glimpse_warp_bytes(int N) { return GNS * G_SLICE + ((N * NH * 4 + 15) & ~15); }
 
 // true when the episode was over before step trel: nobody was unfinished at the previous step
 __device__ __forceinline__ bool episode_over(const RolloutParams& p, int trel) {
@@ -28,30 +39,32 @@ __device__ __forceinline__ bool episode_over(const RolloutParams& p, int trel) {
 }
 
 // ---------------------------------------------------------------- glimpse: tables -> softmax -> c
-__global__ void __launch_bounds__(SW * 32, 2) k_step_glimpse(const RolloutParams p, int t) {
-  extern __shared__ __align__(16) float slots[];   // [SW][QW]: P[n][8], then c[head][dim]
+__global__ void __launch_bounds__(GW_MAX * 32, 2) k_step_glimpse(const RolloutParams p, int t) {
+  extern __shared__ __align__(16) unsigned char gsm[];
   const int trel = t - p.t0;
   if (episode_over(p, trel)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.env.N, kind = p.env.kind;
-  const int64_t B = p.env.B, b = (int64_t)blockIdx.x * SW + warp;
+  const int64_t B = p.env.B, b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (b >= B) return;
-  float* slot = slots + warp * QW;
+  unsigned char* ring = gsm + warp * glimpse_warp_bytes(N);
+  float* slot = reinterpret_cast<float*>(ring + GNS * G_SLICE);
   const int g = lane >> 2, tq = lane & 3;
   const float4* hrow = reinterpret_cast<const float4*>(p.h + b * N * E);
-  // The value pass below is bound by the bytes it keeps in flight (measured: 2.8 TB/s of DRAM reads at 16 warps per SM with
-  // one 8-node slice = 4 KB per warp outstanding).  It is software pipelined over two slices, and slice 0 is requested here,
-  // before the dependent chain cur -> table row -> softmax.
-  auto load_slice = [&](int n0, float4 (&va)[4], float4 (&vb)[4]) {
-    const int na = n0 + tq, nbb = n0 + tq + 4;
+  // slice s = node rows 8s .. 8s+7 -> ring stage s % GNS; lane = 16-byte chunk of the row
+  auto issue_slice = [&](int sidx) {
+    unsigned char* dst = ring + (sidx % GNS) * G_SLICE + lane * 16;
 #pragma unroll
-    for (int cq = 0; cq < 4; ++cq) {
-      va[cq] = (na < N) ? __ldg(hrow + na * (E / 4) + 8 * cq + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-      vb[cq] = (nbb < N) ? __ldg(hrow + nbb * (E / 4) + 8 * cq + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int r = 0; r < 8; ++r)
+      if (8 * sidx + r < N) cp_async16(dst + r * G_ROW, hrow + (8 * sidx + r) * (E / 4) + lane);
+    cp_async_commit();
   };
-  float4 va[4], vb[4];
-  load_slice(0, va, vb);
+  const int nsl = (N + 7) / 8;
+#pragma unroll
+  for (int sidx = 0; sidx < GNS; ++sidx) {
+    if (sidx < nsl) issue_slice(sidx);
+    else cp_async_commit();
+  }
   const float lf = (float)p.env.load[b];
   if (p.mask_hist && lane < 4) p.mask_hist[((int64_t)trel * B + b) * 4 + lane] = __ldcg(p.env.mask + b * 4 + lane);
   if (p.load_hist && lane == 0) p.load_hist[(int64_t)trel * B + b] = lf;
@@ -122,17 +135,29 @@ __global__ void __launch_bounds__(SW * 32, 2) k_step_glimpse(const RolloutParams
   }
   __syncwarp();
   // ---- c[head][dim] = sum_n P[n][head] h_n[dim] on the tensor pipe (M = 16 dims, N = 8 heads, K = 8 nodes).
-  // Thread g streams the float4 chunks 8c' + g (dims 32c' + 4g + e) of node rows n0+tq and n0+tq+4; m-tile
+  // Thread g reads the float4 chunks 8c' + g (dims 32c' + 4g + e) of node rows n0+tq and n0+tq+4; m-tile
   // j = 2c' + u has row g <-> dim 32c'+4g+2u and row g+8 <-> dim 32c'+4g+2u+1.  B = P[n][head] from the slot.
   float cacc[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) cacc[j][i] = 0.f;
-  for (int n0 = 0; n0 < N; n0 += 8) {
-    const int na = n0 + tq, nbb = n0 + tq + 4;
-    float4 wa[4], wb[4];   // next slice (all zeros beyond N)
-    load_slice(n0 + 8, wa, wb);
+  for (int sidx = 0; sidx < nsl; ++sidx) {
+    cp_async_wait<GNS - 1>();   // slice sidx has landed (one group per slice, possibly empty, keeps the count uniform)
+    __syncwarp();
+    const int n0 = 8 * sidx, na = n0 + tq, nbb = n0 + tq + 4;
+    const unsigned char* st = ring + (sidx % GNS) * G_SLICE;
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int cq = 0; cq < 4; ++cq) {
+      va[cq] = *reinterpret_cast<const float4*>(st + tq * G_ROW + (8 * cq + g) * 16);
+      vb[cq] = *reinterpret_cast<const float4*>(st + (tq + 4) * G_ROW + (8 * cq + g) * 16);
+      if (na >= N) va[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nbb >= N) vb[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();   // every lane has read the stage before it is refilled
+    if (sidx + GNS < nsl) issue_slice(sidx + GNS);
+    else cp_async_commit();
     uint32_t bh0, bl0, bh1, bl1;
     split_tf32((na < N) ? slot[na * 8 + g] : 0.f, bh0, bl0);      // (k = tq,   n = head g)
     split_tf32((nbb < N) ? slot[nbb * 8 + g] : 0.f, bh1, bl1);    // (k = tq+4, n = head g)
@@ -152,23 +177,24 @@ __global__ void __launch_bounds__(SW * 32, 2) k_step_glimpse(const RolloutParams
         mma_tf32_16x8x8(cacc[2 * cq + u], ah, bh0, bh1);
       }
     }
-#pragma unroll
-    for (int cq = 0; cq < 4; ++cq) { va[cq] = wa[cq]; vb[cq] = wb[cq]; }
   }
-  __syncwarp();  // every lane is done reading P before c overwrites the slot
+  cp_async_wait<0>();
+  __syncwarp();
   // C fragment of m-tile j = 2cq+u: [0] (dim d, head 2tq), [1] (dim d, head 2tq+1), [2] (dim d+1, head 2tq),
-  // [3] (dim d+1, head 2tq+1) with d = 32cq + 4g + 2u  ->  c[head][dim] staged in the slot, then one coalesced copy
+  // [3] (dim d+1, head 2tq+1) with d = 32cq + 4g + 2u  ->  c[head][dim] staged in the (now idle) ring, then one
+  // coalesced copy
+  float* cst = reinterpret_cast<float*>(ring);
 #pragma unroll
   for (int cq = 0; cq < 4; ++cq)
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int d = 32 * cq + 4 * g + 2 * u, j = 2 * cq + u;
-      *reinterpret_cast<float2*>(slot + (2 * tq) * E + d) = make_float2(cacc[j][0], cacc[j][2]);
-      *reinterpret_cast<float2*>(slot + (2 * tq + 1) * E + d) = make_float2(cacc[j][1], cacc[j][3]);
+      *reinterpret_cast<float2*>(cst + (2 * tq) * E + d) = make_float2(cacc[j][0], cacc[j][2]);
+      *reinterpret_cast<float2*>(cst + (2 * tq + 1) * E + d) = make_float2(cacc[j][1], cacc[j][3]);
     }
   __syncwarp();
   float4* dst = reinterpret_cast<float4*>(p.cbuf + b * QW);
-  for (int i = lane; i < QW / 4; i += 32) dst[i] = *reinterpret_cast<const float4*>(slot + 4 * i);
+  for (int i = lane; i < QW / 4; i += 32) dst[i] = *reinterpret_cast<const float4*>(cst + 4 * i);
 }
 
 // ---------------------------------------------------------------- pointer: logits -> action -> environment
@@ -180,7 +206,9 @@ __global__ void __launch_bounds__(SW * 32) k_step_pointer(const RolloutParams p,
   if (episode_over(p, trel)) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.env.N, kind = p.env.kind;
-  const int64_t B = p.env.B, base = (int64_t)blockIdx.x * SW;
+  // the CTAs walk the batch in the opposite direction to the glimpse kernel: the embeddings that kernel read last are
+  // still in L2 when this one starts, and the ones read last here are there for the next step's glimpse kernel
+  const int64_t B = p.env.B, base = (int64_t)(gridDim.x - 1 - blockIdx.x) * SW;
   const int cnt = (int)((B - base < SW) ? (B - base) : SW);
   if (tid == 0) s_anyleft = 0;
   if (warp < cnt) {
@@ -341,10 +369,13 @@ int prepare_split_weights(const float* m_t, float* m_nt, cudaStream_t stream) {
 
 int run_split_steps(const RolloutParams& p, int t_first, const float* m_nt, cudaStream_t stream) {
   const int64_t B = p.env.B;
-  const unsigned grid = (unsigned)((B + SW - 1) / SW);
-  const size_t smem = (size_t)SW * QW * sizeof(float);
+  int gw = G_CTA_SMEM / glimpse_warp_bytes(p.env.N);
+  if (gw > GW_MAX) gw = GW_MAX;
+  const unsigned grid = (unsigned)((B + SW - 1) / SW), ggrid = (unsigned)((B + gw - 1) / gw);
+  const size_t smem = (size_t)gw * glimpse_warp_bytes(p.env.N);
+  VRPX_CUDA(cudaFuncSetAttribute(k_step_glimpse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int t = t_first; t < p.t0 + p.Tmax; ++t) {
-    k_step_glimpse<<<grid, SW * 32, smem, stream>>>(p, t);
+    k_step_glimpse<<<ggrid, gw * 32, smem, stream>>>(p, t);
     VRPX_LAUNCH_CHECK();
     GemmArgs ga{p.cbuf, B, QW, m_nt, E, p.w.m_c, 0, nullptr, nullptr, nullptr, p.qhat};
     int rc = gemm_tc(ga, stream);
