@@ -9,8 +9,9 @@ one batch of synthetic uniform instances.  Prints ONE JSON line (rank 0).  See D
   value      whole-job instance-steps/s with the instances already resident in HBM (Philox on device)
   e2e        the same through the public API with HOST buffers: pinned host arrays -> TSPEnv.from_arrays ->
              agent.evaluate(env) -> costs back on the host, copies inside the timed region
-  roofline   the persistent rollout kernel: algorithmic bytes (512*N+100 per instance-step) / its CUDA
-             event time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  roofline   the decode loop (persistent kernel for steps 0-1, then glimpse / GEMM-B / pointer launches per step):
+             algorithmic bytes (512*N+100 per instance-step) / the CUDA-event time of those launches,
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline / --impl reference
              the CPU restatement of the reference algorithm (oracle/, numpy env + torch-CPU policy, all host
              threads) on a bounded sample of the same workload.  The unmodified Python reference cannot travel to
@@ -360,7 +361,9 @@ def main():
             "e2e": {"value": e2e_inst_steps / (e2e_ms * 1e-3), "unit": "instance-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": n_e2e},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_rollout (persistent decoder+env)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": ("k_rollout (persistent decoder+env, every step)" if a.no_split else
+                                                     "decode loop: k_rollout (steps 0-1) + per step k_step_glimpse, k_gemm_tc4 "
+                                                     "(GEMM-B), k_step_pointer"), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms},
         }

@@ -105,24 +105,26 @@ __global__ void __launch_bounds__(GW_MAX * 32, 2) k_step_glimpse(const RolloutPa
       }
     }
   }
-  // ---- softmax per head over nodes (lane = node, 4 strides cover N <= 128)
+  // ---- softmax per head over nodes (lane = node; only the ceil(N / 32) strides that hold nodes are touched)
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh) {
-    float mx = -INFINITY;
+    float mx = pr[hh][0];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mx = fmaxf(mx, pr[hh][i]);
+    for (int i = 1; i < 4; ++i)
+      if (32 * i < N) mx = fmaxf(mx, pr[hh][i]);
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = lane + 32 * i;
-      pr[hh][i] = (n < N) ? expf(pr[hh][i] - mx) : 0.f;
-      sum += pr[hh][i];
-    }
+    for (int i = 0; i < 4; ++i)
+      if (32 * i < N) {
+        pr[hh][i] = expf(pr[hh][i] - mx);   // exp(-inf) = 0 for the lanes beyond N
+        sum += pr[hh][i];
+      }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pr[hh][i] *= inv;
+    for (int i = 0; i < 4; ++i)
+      if (32 * i < N) pr[hh][i] *= inv;
   }
   // probabilities to the slot as P[n][8]
 #pragma unroll
