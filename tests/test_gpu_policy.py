@@ -296,3 +296,39 @@ def test_baseline_config_sizes_properties(kind, N, B, greedy):
     if logp is not None:
         lp = logp.cpu().numpy()
         assert np.isfinite(lp).all() and (lp <= 0).all()
+
+
+@pytest.mark.parametrize("kind,N,B", [("tsp", 50, 1000), ("vrp", 30, 517), ("irp", 40, 300)])
+def test_split_step_launches_match_persistent_kernel(kind, N, B):
+    """Table mode runs the decode steps >= 2 either inside the persistent kernel or as glimpse / batched GEMM-B / pointer
+    launches per step (csrc/rollout_steps.cu, the default).  Same arithmetic up to the summation order of GEMM-B: on a
+    teacher-forced tape the masked logits agree to 1e-5, the sampled log-probs too, and the step counts are equal
+    (VRP / IRP episodes end early: the remaining launches must be no-ops)."""
+    import vrpx
+
+    Env, Agent = _cls(kind)
+    agent = Agent(seed=9)
+    agent.model.eval()
+    env = Env(N, B, 0, seed=21, instance_rng="philox")
+    L = vrpx.lib()
+    try:
+        L.vrpx_debug_rollout_split(0)
+        torch.manual_seed(3)
+        with torch.no_grad():
+            loss0, logp0 = agent.model(env, rollout=False, want_logits=True)
+        out0 = agent.model.last_rollout
+        tape, ref, T0 = out0["tape"].cpu().numpy(), out0["logits"].cpu().numpy(), out0["steps"]
+        L.vrpx_debug_rollout_split(1)
+        env.restart_episode()
+        with torch.no_grad():
+            loss1, logp1 = agent.model(env, rollout=False, tape=tape, want_logits=True)
+        out1 = agent.model.last_rollout
+    finally:
+        L.vrpx_debug_rollout_split(1)
+    assert out1["steps"] == T0
+    got = out1["logits"].cpu().numpy()
+    fin = np.isfinite(ref)
+    assert np.array_equal(fin, np.isfinite(got))
+    assert _rel(got[fin], ref[fin]) < 1e-5
+    assert _rel(loss1.cpu().numpy(), loss0.cpu().numpy()) < 1e-5
+    assert np.abs(logp1.cpu().numpy() - logp0.cpu().numpy()).max() < 1e-4 * max(1.0, float(T0)) ** 0.5
