@@ -154,8 +154,13 @@ __global__ void __launch_bounds__(GW_MAX * 32, 2) k_step_glimpse(const RolloutPa
     for (int cq = 0; cq < 4; ++cq) {
       va[cq] = *reinterpret_cast<const float4*>(st + tq * G_ROW + (8 * cq + g) * 16);
       vb[cq] = *reinterpret_cast<const float4*>(st + (tq + 4) * G_ROW + (8 * cq + g) * 16);
-      if (na >= N) va[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (nbb >= N) vb[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (n0 + 8 > N) {   // uniform: only the last slice has rows beyond N (stale ring contents)
+#pragma unroll
+      for (int cq = 0; cq < 4; ++cq) {
+        if (na >= N) va[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nbb >= N) vb[cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     __syncwarp();   // every lane has read the stage before it is refilled
     if (sidx + GNS < nsl) issue_slice(sidx + GNS);

@@ -45,15 +45,10 @@ __global__ void __launch_bounds__(128) k_score_table(const float* __restrict__ q
   }
   __syncwarp();
   const bool vec_ok = (N & 1) == 0;
-  for (int l0 = 0; l0 < N; l0 += 16) {
+  // A fragments of the three k16 steps of a 16-row tile of q': a0 (row la, dims 16c+2t, +1), a1 (row lb, same), a2 (row la,
+  // dims 16c+2t+8, +9), a3 (row lb, same).  The rows of the NEXT tile are requested before the current one is multiplied.
+  auto load_q = [&](int l0, float2 (&qa)[3][2], float2 (&qb)[3][2]) {
     const int la = l0 + g, lb = l0 + g + 8;
-    float acc[NT8][4];
-#pragma unroll
-    for (int j = 0; j < NT8; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-    // A fragments of the three k16 steps: a0 (row la, dims 16c+2t, +1), a1 (row lb, same), a2 (row la, dims 16c+2t+8, +9), a3
-    float2 qa[3][2], qb[3][2];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -63,6 +58,22 @@ __global__ void __launch_bounds__(128) k_score_table(const float* __restrict__ q
         qb[c][u] = (lb < N) ? __ldg(reinterpret_cast<const float2*>(qkb + (size_t)lb * QKW + warp * DQK + 16 * c + 2 * t + 8 * u))
                             : make_float2(0.f, 0.f);
       }
+  };
+  float2 qna[3][2], qnb[3][2];
+  load_q(0, qna, qnb);
+  for (int l0 = 0; l0 < N; l0 += 16) {
+    const int la = l0 + g, lb = l0 + g + 8;
+    float acc[NT8][4];
+#pragma unroll
+    for (int j = 0; j < NT8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    float2 qa[3][2], qb[3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { qa[c][u] = qna[c][u]; qb[c][u] = qnb[c][u]; }
+    load_q(l0 + 16, qna, qnb);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const uint2 s0 = split_f16x2_u(qa[c][0].x, qa[c][0].y), s1_ = split_f16x2_u(qb[c][0].x, qb[c][0].y);
