@@ -223,32 +223,59 @@ __global__ void __launch_bounds__(SW * 32) k_step_pointer(const RolloutParams p,
     float* slot = s_slot[warp];
     const float4 qh = __ldcg(reinterpret_cast<const float4*>(p.qhat + b * E) + lane);
     const float4* hp = reinterpret_cast<const float4*>(p.h + b * N * E) + lane;
+    // own mask (graph_decoder.py:98).  The logits of masked nodes are never used (they become -inf below), so only the
+    // embedding rows of the CANDIDATE nodes are read: on average half of the instance over an episode.
+    uint32_t mw[4], cand[4];
+    int cum[5];
+    cum[0] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mw[i] = __ldcg(p.env.mask + b * 4 + i);
+      const int rem = N - 32 * i;   // nodes of this word
+      const uint32_t range = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+      cand[i] = ~mw[i] & range;
+      cum[i + 1] = cum[i] + __popc(cand[i]);
+    }
+    const int total = cum[4];
+    // lanes 0..7 resolve the node index of candidate j0 + lane (-1 beyond the list)
+    auto resolve = [&](int j0) {
+      int idx = -1;
+      const int j = j0 + lane;
+      if (lane < 8 && j < total) {
+        const int w = (j >= cum[1]) + (j >= cum[2]) + (j >= cum[3]);
+        const uint32_t word = w == 0 ? cand[0] : (w == 1 ? cand[1] : (w == 2 ? cand[2] : cand[3]));
+        const int base_cnt = w == 0 ? 0 : (w == 1 ? cum[1] : (w == 2 ? cum[2] : cum[3]));
+        idx = 32 * w + (int)__fns(word, 0, j - base_cnt + 1);
+      }
+      return idx;
+    };
     {
+      int myidx = resolve(0);
       float4 nxt[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) nxt[i] = (i < N) ? __ldg(hp + i * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int n0 = 0; n0 < N; n0 += 8) {
+      for (int i = 0; i < 8; ++i) {
+        const int n = __shfl_sync(0xffffffffu, myidx, i);
+        nxt[i] = (n >= 0) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int j0 = 0; j0 < total; j0 += 8) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 hv = nxt[i];
           v[i] = fmaf(qh.x, hv.x, fmaf(qh.y, hv.y, fmaf(qh.z, hv.z, qh.w * hv.w)));
         }
+        const int nsel = __shfl_sync(0xffffffffu, myidx, (lane >> 2) & 7);   // node of the sum this lane group reduces
+        myidx = resolve(j0 + 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int n = n0 + 8 + i;
-          nxt[i] = (n < N) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int n = __shfl_sync(0xffffffffu, myidx, i);
+          nxt[i] = (n >= 0) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float sc = reduce8(v, lane);
-        const int n = n0 + ((lane >> 2) & 7);
-        if ((lane & 3) == 0 && n < N) slot[n] = 10.0f * tanhf(sc);
+        if ((lane & 3) == 0 && nsel >= 0) slot[nsel] = 10.0f * tanhf(sc);
       }
     }
     __syncwarp();
-    // own mask (graph_decoder.py:98), 4 consecutive nodes per lane
-    uint32_t mw[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) mw[i] = __ldcg(p.env.mask + b * 4 + i);
     float u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
