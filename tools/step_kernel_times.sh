@@ -1,7 +1,7 @@
 #!/bin/bash
 # Per-kernel durations of three split decode steps of the bench workload (ncu, cold-cache / serialised: use for shares).
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,sm__warps_active.avg.per_cycle_active --clock-control none \
-    -k regex:"k_step_glimpse|k_step_pointer|k_gemm_tc4" -s 700 -c 9 --csv --log-file gpurun_out/steps9.csv \
+    -k regex:"k_step_glimpse|k_step_pointer|k_gemm_tc4" -s 700 -c 6 --csv --log-file gpurun_out/steps9.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
