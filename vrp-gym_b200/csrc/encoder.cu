@@ -214,12 +214,6 @@ __global__ void __launch_bounds__(256) k_enc_attention(const float* __restrict__
 //      dim stride padded by 4 chunks (the LDS.128 of a quarter warp — dims g in {2q, 2q+1}, t = 0..3 — is conflict free)
 //      and chunk position XOR 4 on every other group of 4 dims (so are the staging stores: dims d and d + 4 per quarter)
 // NJJ = ceil(N / 16) k16 steps over the keys (compile-time bound on the registers).
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 template <int NJJ>
 __global__ void __launch_bounds__(256) k_enc_attention_f16(const float* __restrict__ qkv, float* __restrict__ att, int N) {
   extern __shared__ __align__(16) uint4 smf[];

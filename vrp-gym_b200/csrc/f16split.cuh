@@ -44,4 +44,11 @@ __device__ __forceinline__ uint2 split_f16x2_u(float x0, float x1) {
   return make_uint2(*reinterpret_cast<const uint32_t*>(&h), *reinterpret_cast<const uint32_t*>(&l));
 }
 
+// 2^x, hardware approximation (relative error ~2^-22); 2^-inf = 0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 }  // namespace vrpx

@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(GW_MAX * 32, 2) k_step_glimpse(const RolloutPa
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (32 * i < N) {
-        pr[hh][i] = expf(pr[hh][i] - mx);   // exp(-inf) = 0 for the lanes beyond N
+        pr[hh][i] = expf(pr[hh][i] - mx);   // exp(-inf) = 0 for the lanes beyond N (ex2.approx was measured: no time gained,
+                                            // mean logit error 4x larger)
         sum += pr[hh][i];
       }
     sum = warp_sum(sum);
