@@ -1,4 +1,5 @@
-"""Per-phase cycle breakdown of the persistent rollout kernel (debug counters, thread 0 of every CTA)."""
+"""Per-phase cycle breakdown of the persistent rollout kernel (debug counters, thread 0 of every CTA).
+The split-step launches are switched off so that every decode step runs inside the persistent kernel."""
 import ctypes as C
 import os
 import sys
@@ -20,6 +21,7 @@ buf = torch.zeros(8, dtype=torch.int64, device="cuda")
 L = vrpx.lib()
 L.vrpx_debug_rollout_profile.argtypes = [C.c_void_p]
 L.vrpx_debug_rollout_profile.restype = None
+L.vrpx_debug_rollout_split(0)
 with torch.no_grad():
     for rep in range(3):
         env.restart_episode()

@@ -34,13 +34,6 @@ constexpr int RNST = 2;   // depth of the per-warp weight rings of the tile GEMM
 constexpr size_t SMEM_W_RING = (size_t)(NT / 32) * RNST * 512 * sizeof(float);   // 64 KiB
 constexpr size_t SMEM_TOTAL = SMEM_X_MMA + SMEM_QC_MMA + SMEM_W_RING;
 
-// Pull one instance's embeddings (N rows of 512 B) towards L2 ahead of their first use in a step: the first pass over
-// h would otherwise pay HBM latency on every row tile.
-__device__ __forceinline__ void prefetch_instance_l2(const float* hb, int N, int lane) {
-  const char* base = reinterpret_cast<const char*>(hb);
-  for (int i = lane; i < N * 4; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
-}
-
 // m_t [1024][128] f32 -> M16 [512 k-pairs][128] {hi2, lo2}: the B operand of the fp16-split GEMM-B (tile_gemm.cuh)
 __global__ void k_split_m16(const float* __restrict__ m_t, uint2* __restrict__ m16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // kp * 128 + n
