@@ -356,7 +356,7 @@ def main():
                        "l2": "inputs larger than L2 (embeddings %.2f GB per GPU re-streamed every decode step)" % (B * N * 512 / 1e9)},
             "rollouts_per_sec": value / T,
             "mean_cost": mean_cost,
-            "breakdown_ms": {"encoder": enc_ms, "score_tables": roll_ms - kern_ms, "rollout_kernel": kern_ms},
+            "breakdown_ms": {"encoder": enc_ms, "score_tables": roll_ms - kern_ms, "decode_loop": kern_ms},
             "clocks": clk,
             "e2e": {"value": e2e_inst_steps / (e2e_ms * 1e-3), "unit": "instance-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": n_e2e},
