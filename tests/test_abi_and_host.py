@@ -114,3 +114,58 @@ def test_state_dict_layout_matches_reference_keys():
         assert len(sd) == 69
         assert sd["encoder.node_embed.weight"].shape == (128, f)
         assert sd["encoder.depot_embed.weight"].shape == (128, 2)
+
+
+# ---- sizes of the rollout workspace (pure arithmetic entry points: callable without a GPU)
+def test_rollout_workspace_layout_is_consistent():
+    import vrpx
+
+    L = vrpx.lib()
+    off = int(L.vrpx_rollout_workspace_qg_offset())
+    assert off % 256 == 0 and off >= 4096 + 512 * 1024      # header + pre-split m_t in front of the Q~g table
+    for kind in (vrpx.TSP, vrpx.VRP, vrpx.IRP):
+        prev_plain = prev_table = 0
+        for B, N in [(1, 4), (64, 20), (4096, 40), (65536, 50), (131072, 100)]:
+            plain = int(L.vrpx_rollout_workspace_bytes(B, N))
+            table = int(L.vrpx_rollout_table_workspace_bytes(kind, B, N))
+            assert plain == off + B * 1024 * 4                # Q~g [B][1024] f32 right behind the header
+            # the table workspace also holds S0 (, SL), S1 [B][N][8][N], a QK slice, c [B][1024], q^ [B][128], m_t^T
+            floor = plain + B * 8 * N * 4 + B * N * 8 * N * 4 + B * 1024 * 4 + B * 128 * 4 + 1024 * 128 * 4
+            assert table >= floor, (kind, B, N, table, floor)
+            assert table % 256 == 0
+            assert plain > prev_plain and table > prev_table
+            prev_plain, prev_table = plain, table
+        if kind == vrpx.IRP:                                  # IRP carries the extra load table SL [B][8][N]
+            assert int(L.vrpx_rollout_table_workspace_bytes(vrpx.IRP, 4096, 40)) > int(
+                L.vrpx_rollout_table_workspace_bytes(vrpx.TSP, 4096, 40))
+
+
+# ---- precision policy of the tensor-core contractions (csrc/f16split.cuh), restated in numpy
+def _split_f16(x, scale):
+    hi = x.astype(np.float16)
+    lo = ((x - hi.astype(np.float32)) * np.float32(scale)).astype(np.float16)
+    return hi, lo
+
+
+@pytest.mark.parametrize("scale", [1.0, 2048.0], ids=["unscaled_lo", "scaled_lo"])
+def test_f16_hi_lo_split_keeps_fp32_accuracy(scale):
+    """x = hi + lo / scale with hi = f16(x), lo = f16((x - hi) * scale) carries ~22 significant bits, and the three-term
+    product hi·hi + (lo·hi + hi·lo) / scale reproduces an fp32 dot product to ~1e-6 of its scale (the kernels accumulate
+    in fp32 on the tensor cores; here float64 sums isolate the operand error)."""
+    rs = np.random.RandomState(0)
+    x = (rs.randn(256, 512) * 2.0).astype(np.float32)          # activations after BatchNorm: O(1)
+    w = (rs.randn(512, 64) / np.sqrt(512)).astype(np.float32)  # weights: O(1/sqrt(K))
+    if scale == 1.0:
+        w = w * np.float32(256.0)                              # the GEMM scales W by 2^8 before the unscaled split
+    xh, xl = _split_f16(x, scale)
+    wh, wl = _split_f16(w, scale)
+    rec = xh.astype(np.float64) + xl.astype(np.float64) / scale
+    big = np.abs(x) >= 0.25                                    # below, an unscaled lo is a subnormal f16: absolute 2^-25
+    assert np.max(np.abs(rec - x)[big] / np.abs(x)[big]) < 2.0 ** -21
+    assert np.max(np.abs(rec - x)) < 2.0 ** -20 * np.abs(x).max()
+    f = lambda a: a.astype(np.float64)
+    got = f(xh) @ f(wh) + (f(xl) @ f(wh) + f(xh) @ f(wl)) / scale
+    ref = f(x) @ f(w)
+    assert np.max(np.abs(got - ref)) < 2e-6 * np.abs(ref).max()
+    # a single f16 (or TF32) pass would miss the bar by three orders of magnitude
+    assert np.max(np.abs(f(xh) @ f(wh) - ref)) > 1e-4 * np.abs(ref).max()
