@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak scaling)")
     ap.add_argument("--coupling", type=int, default=-1, help="glimpse-mask coupling group; -1 = whole per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="instances in the bounded CPU sample")
-    ap.add_argument("--gemm-path", type=int, default=0, help="0 tcgen05 f16-split (production), 1 fp32 SIMT, 2 tcgen05 3xTF32")
+    ap.add_argument("--gemm-path", type=int, default=0, help="0 tcgen05 f16-split (production), 1 fp32 SIMT cross-check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-split", action="store_true",
                     help="keep every decode step inside the persistent kernel (A/B against the split-step launches)")

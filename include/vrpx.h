@@ -25,7 +25,7 @@ extern "C" {
 #define VRPX_API
 #endif
 
-#define VRPX_ABI_VERSION 3
+#define VRPX_ABI_VERSION 4
 #define VRPX_MAX_NODES 128 /* visited bitmask = 4 x u32 per instance */
 #define VRPX_EMB 128       /* embedding width E (graph_tsp_agent.py:98) */
 #define VRPX_HEADS 8       /* heads (graph_tsp_agent.py:101, :55) */
@@ -91,6 +91,29 @@ VRPX_API int vrpx_env_observe(const vrpx_env* env, double* state, double* mask, 
 /* Write back a (B,N) f64 0/1 array into the bitmask (used when a caller assigns env.visited). */
 VRPX_API int vrpx_env_set_visited(const vrpx_env* env, const double* visited, void* stream);
 
+/* Recompute the decoder-visible IRP mask = visited | (demand - load > 0) (irp.py:151-155) from the CURRENT demand /
+ * load arrays, e.g. after a caller edited node demands through sampler.graphs[i].nodes[n]["demand"] (the write-through
+ * protocol of tests/test_env.py:31-36).  No-op for TSP / VRP (mask aliases visited). */
+VRPX_API int vrpx_env_refresh_mask(const vrpx_env* env, void* stream);
+
+/* ---------------------------------------------------------------- seed-compatible instance stream (host, C)
+ * The reference draws instances from numpy's legacy global RandomState (MT19937) one graph after the other
+ * (gym_vrp/graph/vrp_graph.py:29,34,42 via vrp_network.py:41-42, after tsp.py:48,55).  These entry points consume a COPY
+ * of that generator state — key[624] + pos, the layout of np.random.get_state() — exactly as numpy would and leave the
+ * advanced state in place, so the caller hands it back with np.random.set_state().  Host pointers (h_*), no GPU needed.
+ *   vrpx_mt19937_seed              np.random.seed(seed) for 0 <= seed < 2^32
+ *   vrpx_mt19937_permutation_head  np.random.choice(n, k, replace=False) = permutation(n)[:k]   (tsp.py:55 draw_idxs)
+ *   vrpx_mt19937_instances         per graph: rand(N,2) -> choice(N, D, replace=False) -> uniform(1,10,(N,1))/C, depot
+ *                                  demand 0; h_xy [G][N][2] f64, h_depots [G][D] int64, h_demand [G][N] f64
+ *   vrpx_mt19937_random_actions    RandomAgent (agents/random_agent.py:33-35): per instance np.random.choice(feasible, 1)
+ *                                  with feasible = nodes whose mask entry is 0; h_mask [B][N] f64, h_actions [B] int64 */
+VRPX_API int vrpx_mt19937_seed(uint32_t seed, uint32_t* key, int32_t* pos);
+VRPX_API int vrpx_mt19937_permutation_head(uint32_t* key, int32_t* pos, int64_t n, int64_t k, int64_t* h_out);
+VRPX_API int vrpx_mt19937_instances(uint32_t* key, int32_t* pos, int64_t num_graphs, int32_t N, int32_t num_depots,
+                                    double* h_xy, int64_t* h_depots, double* h_demand);
+VRPX_API int vrpx_mt19937_random_actions(uint32_t* key, int32_t* pos, const double* h_mask, int64_t B, int32_t N,
+                                         int64_t* h_actions);
+
 /* ---------------------------------------------------------------- policy */
 
 /* Encoder parameters, torch layouts (row-major [out][in]) — state_dict keys of SURVEY App. A.5. */
@@ -123,7 +146,8 @@ VRPX_API int64_t vrpx_encoder_workspace_bytes(int64_t B, int32_t N);
  *   train  0: running statistics; 1: batch statistics over all B*N rows + running-stat update
  *          (momentum 0.1, unbiased variance), graph_encoder.py:150-154;
  *   h      [B][N][128] f32 output embeddings;
- *   gemm_path 0: tcgen05 3xTF32 tensor-core GEMMs; 1: fp32 SIMT GEMMs (debug / cross-check);
+ *   gemm_path 0: tcgen05 kind::f16 GEMMs on f16 hi/lo operand halves (~fp32 accuracy, production);
+ *             1: fp32 SIMT GEMMs (debug / cross-check);
  *   saved  NULL, or (train mode) a buffer of vrpx_encoder_saved_bytes() that receives the activations the
  *          backward pass needs. */
 VRPX_API int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, const float* x,
@@ -211,7 +235,8 @@ VRPX_API int64_t vrpx_rollout_table_workspace_bytes(int32_t kind, int64_t B, int
  *   mode     greedy argmax (graph_decoder.py:103), Philox sampling (:105-107), or teacher-forced
  *   coupling glimpse-mask coupling group G (graph_decoder.py:93 `mask.repeat(H,1)`): attention row (b,h)
  *            adds mask[g0 + ((b-g0)*8+h) mod G], g0 = floor(b/G)*G.  G == B is the reference at batch B;
- *            0 disables the quirk's scrambling (adds the instance's own mask) — NOT reference-equal.
+ *            0 disables the quirk's scrambling (adds the instance's own mask) — NOT reference-equal.  Any other value
+ *            must divide B (VRPX_ERR_ARG otherwise: the partner row would fall outside the batch).
  *   tape     [Tmax][B] uint8 actions: written (greedy/sample) or read (teacher); may be NULL unless teacher
  *   t_begin  first step to execute: 0 starts an episode (builds the per-episode tables in `ws`); > 0 resumes
  *            one whose `ws`, env state, logp and cost were left by the previous call (single-step decoding)
@@ -276,7 +301,7 @@ VRPX_API int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B
 VRPX_API int vrpx_episode_scatter(float* dH, const uint8_t* tape0, int64_t B, int32_t N, const float* dG, const float* dXf,
                                   void* stream);
 
-/* Test hook (tests/test_gemm.py): Y[R][NOUT] = epilogue(X[R][K] · W[NOUT][K]^T) through the tcgen05 3xTF32
+/* Test hook (tests/test_gpu_gemm.py): Y[R][NOUT] = epilogue(X[R][K] · W[NOUT][K]^T) through the tcgen05 f16-split
  * path (path 0) or the fp32 SIMT path (path 1); epilogue = +bias, ReLU, +residual, *scale+shift (each optional). */
 VRPX_API int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float* W, int32_t NOUT, const float* bias,
                              int32_t relu, const float* residual, const float* scale, const float* shift, float* Y,

@@ -129,7 +129,9 @@ class EnvOracle:
         return np.dstack([self.xy, is_depot, mask])
 
     # tsp.py:60-101 ; irp.py:49-99
-    def step(self, actions):
+    def step(self, actions, observe=True):
+        """observe=False skips building the (B,N,4|5) observation (the mask rules still run, as the reference's
+        get_state call inside step would run them): for replaying long tapes at large batches in tests."""
         a = np.asarray(actions).reshape(self.B).astype(np.int64)
         ar = self._ar
         self.step_count += 1
@@ -143,6 +145,9 @@ class EnvOracle:
             self.load[a == self.depot] = 1  # irp.py:86
         self.cur = a  # tsp.py:90
         done = self.is_done()  # BEFORE the mask rules (tsp.py:95)
+        if not observe:
+            self.generate_mask()
+            return None, -dist, done, None
         state = self.get_state()  # applies MASK() (tsp.py:97)
         return state, -dist, done, None
 

@@ -62,12 +62,16 @@ def encoder_forward(sd, x, depot_onehot=None, train=False, num_layers=3):
     return h
 
 
-def decoder_logits(sd, h, mask, first, last, load=None, C=10.0):
+def decoder_logits(sd, h, mask, first, last, load=None, C=10.0, glimpse_mask=None):
     """One decode step up to the masked pointer logits — graph_decoder.py:75-98.
 
     h (B,N,E); mask (B,N) f32 0/1; first/last (B,E).  Returns u (B,N) with -inf on
     masked nodes.  Includes the additive, head-scrambled glimpse mask (:93-94):
     attention row (b,h) adds mask[(b*H+h) mod B].
+
+    glimpse_mask (B,H,N), optional: the rows `mask.repeat(H,1)` would deliver, given
+    explicitly — lets a test evaluate a SUBSET of a large batch (the rows of the
+    partner instances (b*H+h) mod B_full are looked up by the caller).
     """
     B, N, E = h.shape
     D = 3 * E
@@ -86,8 +90,10 @@ def decoder_logits(sd, h, mask, first, last, load=None, C=10.0):
     K = K.view(B, N, H, dh).permute(0, 2, 1, 3)
     V = V.view(B, N, H, dh).permute(0, 2, 1, 3)
     s = torch.einsum("bhd,bhnd->bhn", q, K) / math.sqrt(dh)
-    rows = (torch.arange(B)[:, None] * H + torch.arange(H)[None, :]) % B  # mask.repeat(H,1) quirk
-    s = s + mask[rows]  # float mask is ADDED (:93-94)
+    if glimpse_mask is None:
+        rows = (torch.arange(B)[:, None] * H + torch.arange(H)[None, :]) % B  # mask.repeat(H,1) quirk
+        glimpse_mask = mask[rows]
+    s = s + glimpse_mask  # float mask is ADDED (:93-94)
     p = torch.softmax(s, dim=-1)
     a = torch.einsum("bhn,bhnd->bhd", p, V).reshape(B, D)
     o = a @ sd["decoder.attention.out_proj.weight"].T + sd["decoder.attention.out_proj.bias"]
@@ -162,7 +168,46 @@ def rollout(sd, env: EnvOracle, greedy=True, train=False, tape=None, return_trac
     return acc_loss, acc_logp
 
 
+def replay_subset_logits(sd, h, tape, own_masks, glimpse_masks, loads=None):
+    """Teacher-forced per-step pointer logits of a SUBSET of a (possibly huge) batch — graph_decoder.py:75-115 looped as
+    in graph_tsp_agent.py:78-88.
+
+    h (S,N,E) embeddings of the subset; tape (T,S) the subset's actions; own_masks (T,S,N) each instance's mask before
+    step t; glimpse_masks (T,S,H,N) the masks of its partner rows (b*H+h) mod B_full before step t; loads (T,S) f32
+    (IRP) or None.  Returns logits (T,S,N) and per-step log-probs (T,S)."""
+    S, N, E = h.shape
+    first = sd["decoder._first_node"].reshape(1, E).repeat(S, 1)
+    last = sd["decoder._last_node"].reshape(1, E).repeat(S, 1)
+    out, lps = [], []
+    ar = torch.arange(S)
+    for t in range(tape.shape[0]):
+        u = decoder_logits(sd, h, torch.as_tensor(own_masks[t], dtype=torch.float), first, last,
+                           None if loads is None else torch.as_tensor(loads[t], dtype=torch.float),
+                           glimpse_mask=torch.as_tensor(glimpse_masks[t], dtype=torch.float))
+        a = torch.as_tensor(tape[t], dtype=torch.long)
+        lps.append((u.gather(1, a[:, None])[:, 0] - torch.logsumexp(u, dim=-1)).numpy())
+        last = h[ar, a]
+        if t == 0:
+            first = last
+        out.append(u.numpy())
+    return np.stack(out), np.stack(lps)
+
+
 def reinforce_loss(cost_model, cost_baseline, logp):
     """graph_tsp_agent.py:179-180 with loss_* = -cost: advantage = cost_m - cost_b."""
     adv = cost_model - cost_baseline
     return (adv * logp).mean()
+
+
+def reinforce_gradients(kind, sd, xy, depot, demand, tape, baseline):
+    """torch autograd through the oracle's train-mode teacher-forced rollout: loss = mean((cost_m - cost_b) * log_prob)
+    (graph_tsp_agent.py:179-186).  Returns {parameter name: gradient} for every parameter with a gradient."""
+    sd = {k: v.detach().clone() for k, v in sd.items()}
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and "running_" not in k:
+            v.requires_grad_(True)
+    loss_m, logp = rollout(sd, EnvOracle(kind, xy, depot, demand), greedy=False, train=True, tape=tape)
+    adv = (loss_m.detach() - torch.as_tensor(baseline)) * -1
+    loss = (adv * logp).mean()
+    loss.backward()
+    return {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}, float(loss.item())

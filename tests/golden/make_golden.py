@@ -10,6 +10,7 @@ Outputs (all small, committed):
   env_tapes.npz           per-step transitions of reference TSPEnv/VRPEnv/IRPEnv under recorded actions
   policy_<kind>.npz       embeddings / per-step logits / greedy tapes / costs / teacher-forced log-probs
                           from reference {TSP,VRP,IRP}Agent(seed) with seed-initialised weights
+  policy_<kind>_large.npz the same at the benchmarked node counts N = 40 / 50 / 100 (B = 8)
   known_answers.json      constants asserted by the reference's own tests + SURVEY App. C
 """
 import csv
@@ -147,10 +148,15 @@ def _weights_checksum(sd):
     return float(sum(v.double().sum().item() for v in sd.values()))
 
 
-def policy_traces():
+SMALL_CASES = ((4, 2, 69), (10, 8, 7), (20, 32, 1234))
+# the node counts the benchmarks run (BASELINE.json configs 3-5: N = 40 / 50 / 100) at a batch the reference plays in seconds
+LARGE_CASES = ((40, 8, 30), (50, 8, 31), (100, 8, 32))
+
+
+def policy_traces(cases=SMALL_CASES, suffix=""):
     for kind in ("tsp", "vrp", "irp"):
         out = {}
-        for (N, B, seed) in ((4, 2, 69), (10, 8, 7), (20, 32, 1234)):
+        for (N, B, seed) in cases:
             key = f"{N}_{B}_{seed}"
             env = ENVS[kind](N, B, 1, seed)
             agent = AGENTS[kind](seed=seed)
@@ -171,7 +177,7 @@ def policy_traces():
             out[key + "/greedy_actions"] = np.stack(acts).astype(np.int64)
             out[key + "/greedy_logits"] = np.stack(rec.logits).astype(np.float32)
             out[key + "/greedy_loss"] = cost.numpy()
-            out[key + "/emb_eval"] = embs[-1][: min(B, 4)]
+            out[key + "/emb_eval"] = embs[-1][: min(B, 4)] if not suffix else embs[-1]
             # teacher-forced sampled-mode log-probs (eval-mode BN) along a random feasible tape
             env_t = deepcopy(env)
             rs = np.random.RandomState(3)
@@ -216,7 +222,7 @@ def policy_traces():
             loss = (adv * logp_m).mean()  # :180
             agent2.opt.zero_grad()
             loss.backward()
-            out[key + "/train_emb"] = embs2[-1][: min(B, 4)]
+            out[key + "/train_emb"] = embs2[-1][: min(B, 4)] if not suffix else embs2[-1]
             out[key + "/train_logp"] = logp_m.detach().numpy()
             out[key + "/train_loss"] = np.float32(loss.item())
             for name, p in agent2.model.named_parameters():
@@ -229,8 +235,8 @@ def policy_traces():
             out[key + "/bn_l0_running_mean"] = bn.running_mean.numpy().copy()
             out[key + "/bn_l0_running_var"] = bn.running_var.numpy().copy()
             hook.remove()
-        np.savez_compressed(os.path.join(HERE, f"policy_{kind}.npz"), **out)
-        print(f"policy_{kind}.npz:", len(out), "arrays")
+        np.savez_compressed(os.path.join(HERE, f"policy_{kind}{suffix}.npz"), **out)
+        print(f"policy_{kind}{suffix}.npz:", len(out), "arrays")
 
 
 # ---------------------------------------------------------------- 4. known answers
@@ -264,7 +270,11 @@ def known_answers():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        policy_traces(LARGE_CASES, "_large")
+        sys.exit(0)
     golden_random_costs()
     env_tapes()
     policy_traces()
+    policy_traces(LARGE_CASES, "_large")
     known_answers()

@@ -13,6 +13,7 @@ between calls exactly like the reference module does.
 from __future__ import annotations
 
 import ctypes as C
+import logging
 
 import numpy as np
 import torch
@@ -78,10 +79,17 @@ class GraphDecoder(nn.Module):
             try:
                 ws, nbytes = torch.empty((tbytes,), dtype=torch.uint8, device=dev), tbytes
             except torch.cuda.OutOfMemoryError:
+                # not silent: the classic per-step score pass is the same arithmetic but ~2x slower
+                logging.getLogger(__name__).warning(
+                    "vrpx: %.1f GiB score-table workspace does not fit on %s; this rollout runs the classic decode "
+                    "loop (set decoder.score_tables = False to choose it explicitly)", tbytes / 2 ** 30, dev)
                 ws = None
         if ws is None:
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         G = B if coupling is None else int(coupling)
+        if G < 0 or (G != 0 and (G > B or B % G != 0)):
+            raise ValueError(f"coupling group {G} must be 0 or a divisor of the batch size {B}: attention row (b, head) "
+                             "reads the mask of instance (8b + head) mod G of its group (graph_decoder.py:93)")
         trace, saved = None, None
         if save_for_backward:
             saved = {"mask_hist": torch.empty((Tmax, B, 4), dtype=torch.int32, device=dev),

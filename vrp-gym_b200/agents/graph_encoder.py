@@ -5,7 +5,7 @@ checkpoints interchange and `torch.manual_seed(s)` yields the same initial weigh
     encoder.node_embed, [encoder.depot_embed], encoder.attention_layers.{0,1,2}.{attention_layer, bn1.norm,
     bn2.norm, ff.0, ff.2}.
 The arithmetic (embedding, 3 x {MHA + skip + BatchNorm, FF + skip + BatchNorm}) is `vrpx_encoder_forward`:
-tcgen05 tensor-core GEMMs (3xTF32) for the dense layers, a fused per-instance attention kernel, BatchNorm in
+tcgen05 tensor-core GEMMs (kind::f16 on f16 hi/lo operand halves, ~fp32 accuracy) for the dense layers, a fused per-instance attention kernel, BatchNorm in
 eval (running statistics) or train (batch statistics over all B*N rows) mode.
 """
 from __future__ import annotations
@@ -84,7 +84,7 @@ class GraphEncoder(nn.Module):
         self.attention_layers = nn.ModuleList(
             [MultiHeadAttentionLayer(embedding_dim=embedding_dim, hidden_dim=hidden_dim, num_heads=num_heads)
              for _ in range(num_attention_layers)])
-        self.gemm_path = 0  # 0: tcgen05 f16-split, 1: fp32 SIMT cross-check, 2: tcgen05 3xTF32
+        self.gemm_path = 0  # 0: tcgen05 f16-split (production), 1: fp32 SIMT cross-check
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x (num_graphs, num_nodes, f) -> embeddings (num_graphs, num_nodes, 128), on x's device."""

@@ -62,6 +62,8 @@ class TSPModel(nn.Module):
         dev = env._device
         if next(self.parameters()).device != dev:
             self.to(dev)
+        # host-side edits (sampler.graphs[i].nodes[n]["coordinates"] = ...) reach the device BEFORE the encoder reads them
+        env._sync_instances()
         depot = env._depot if self._USES_DEPOT_EMBED else None
         # a sampled rollout of a model in train mode under grad is the REINFORCE forward: keep what backward needs
         need_grad = self.training and torch.is_grad_enabled() and (not rollout)

@@ -37,6 +37,42 @@ void count_launch(int n = 1);
 
 int num_sms();  // multiprocessor count of the current device (cached)
 
+// Every launching entry point runs on the device that OWNS its buffers, not on whatever device happens to be current
+// in the calling thread: the guard looks the owner of a device pointer up (cudaPointerGetAttributes), switches to it
+// and restores the previous device on scope exit.  The stream the caller passes must belong to that device.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(const void* device_ptr) {
+    cudaPointerAttributes a;
+    err = cudaPointerGetAttributes(&a, device_ptr);
+    if (err != cudaSuccess) return;
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) {
+      err = cudaErrorInvalidDevicePointer;
+      return;
+    }
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != a.device) {
+      err = cudaSetDevice(a.device);
+      switched = (err == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define VRPX_DEVICE_GUARD(ptr)                                                                       \
+  vrpx::DeviceGuard device_guard_(ptr);                                                              \
+  if (device_guard_.err != cudaSuccess) {                                                            \
+    vrpx::set_error("%s: %s is not a device pointer this process can use (%s)", __func__, #ptr,      \
+                    cudaGetErrorString(device_guard_.err));                                          \
+    (void)cudaGetLastError();                                                                        \
+    return VRPX_ERR_ARG;                                                                             \
+  }
+
 // ---------------------------------------------------------------- device helpers
 constexpr int E = VRPX_EMB;      // 128
 constexpr int NH = VRPX_HEADS;   // 8

@@ -756,6 +756,10 @@ int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, co
                           const vrpx_decoder_grads* g, void* ws, int64_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(env && w && wb && h && tape && trace && qg && wts && g && ws, "NULL argument");
+  VRPX_DEVICE_GUARD(h);
+  // the glimpse mask of attention row (b, head) is read at quirk_row(): it must stay inside the batch
+  VRPX_CHECK_ARG(coupling >= 0 && (coupling == 0 || (coupling <= env->B && env->B % coupling == 0)),
+                 "coupling group must be 0 or a divisor of the batch size");
   VRPX_CHECK_ARG(env->N >= 2 && env->N <= VRPX_MAX_NODES && env->B >= 1 && T >= 1, "bad shape");
   VRPX_CHECK_ARG(trace->mask_hist && trace->qg0 && (env->kind != VRPX_IRP || trace->load_hist), "trace incomplete");
   VRPX_CHECK_ARG(g->dH && g->D0 && g->D1 && g->d_al_t && g->d_m_t && g->d_m_c && (env->kind != VRPX_IRP || g->Dl),
@@ -779,6 +783,7 @@ int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, co
 
 int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R, int32_t M, int32_t N, void* stream) {
   VRPX_CHECK_ARG(A && Bm && C && R >= 1 && M >= 1 && N >= 1 && M % 4 == 0 && N % 4 == 0, "bad argument");
+  VRPX_DEVICE_GUARD(A);
   int64_t ctas = (R + 2047) / 2048;
   int64_t maxc = (int64_t)num_sms() * 8;
   if (ctas > maxc) ctas = maxc;
@@ -798,6 +803,7 @@ int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R
 
 int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out, void* stream) {
   VRPX_CHECK_ARG(X && out && R >= 1 && Ccols >= 1, "bad argument");
+  VRPX_DEVICE_GUARD(X);
   int64_t ctas = (R + 511) / 512;
   int64_t maxc = (int64_t)num_sms() * 8;
   if (ctas > maxc) ctas = maxc;
@@ -810,6 +816,7 @@ int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out,
 
 int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B, int32_t N, float* G, float* Xf, void* stream) {
   VRPX_CHECK_ARG(h && G && B >= 1 && (Xf == nullptr || tape0 != nullptr), "bad argument");
+  VRPX_DEVICE_GUARD(h);
   k_episode_gather<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(h, tape0, B, N, G, Xf);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
@@ -818,6 +825,7 @@ int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B, int32_t
 int vrpx_episode_scatter(float* dH, const uint8_t* tape0, int64_t B, int32_t N, const float* dG, const float* dXf,
                          void* stream) {
   VRPX_CHECK_ARG(dH && dG && B >= 1 && (dXf == nullptr || tape0 != nullptr), "bad argument");
+  VRPX_DEVICE_GUARD(dH);
   k_episode_scatter<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dH, tape0, B, N, dG, dXf);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;

@@ -154,6 +154,14 @@ __global__ void k_observe(vrpx_env e, double* __restrict__ state, double* __rest
   }
 }
 
+__global__ void k_refresh_mask(vrpx_env e) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= e.B) return;
+  Bits128 x = demand_exceeds(e.demand + b * e.N, e.N, e.load[b]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e.mask[b * 4 + i] = e.visited[b * 4 + i] | x.w[i];
+}
+
 __global__ void k_set_visited(vrpx_env e, const double* __restrict__ visited) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= e.B) return;
@@ -205,6 +213,7 @@ int vrpx_device_check(int device) {
 int vrpx_env_generate(const vrpx_env* env, uint64_t seed, uint64_t offset, void* stream) {
   int rc = check_env(env, __func__);
   if (rc) return rc;
+  VRPX_DEVICE_GUARD(env->xy);
   int64_t n = env->B * env->N;
   k_generate<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*env, seed, offset);
   VRPX_LAUNCH_CHECK();
@@ -214,6 +223,7 @@ int vrpx_env_generate(const vrpx_env* env, uint64_t seed, uint64_t offset, void*
 int vrpx_env_reset(const vrpx_env* env, void* stream) {
   int rc = check_env(env, __func__);
   if (rc) return rc;
+  VRPX_DEVICE_GUARD(env->xy);
   k_reset<<<grid_for(env->B, 256), 256, 0, (cudaStream_t)stream>>>(*env);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
@@ -222,6 +232,7 @@ int vrpx_env_reset(const vrpx_env* env, void* stream) {
 int vrpx_env_observe(const vrpx_env* env, double* state, double* mask, double* visited, void* stream) {
   int rc = check_env(env, __func__);
   if (rc) return rc;
+  VRPX_DEVICE_GUARD(env->xy);
   if (!state && !mask && !visited) return VRPX_OK;
   int64_t n = env->B * env->N;
   k_observe<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*env, state, mask, visited);
@@ -233,6 +244,7 @@ int vrpx_env_step(const vrpx_env* env, const int64_t* actions, double* reward, i
                   double* state, void* stream) {
   int rc = check_env(env, __func__);
   if (rc) return rc;
+  VRPX_DEVICE_GUARD(env->xy);
   VRPX_CHECK_ARG(actions && reward && not_done, "actions/reward/not_done must be non-NULL");
   k_step<<<grid_for(env->B, 256), 256, 0, (cudaStream_t)stream>>>(*env, actions, reward, not_done);
   VRPX_LAUNCH_CHECK();
@@ -240,9 +252,20 @@ int vrpx_env_step(const vrpx_env* env, const int64_t* actions, double* reward, i
   return VRPX_OK;
 }
 
+int vrpx_env_refresh_mask(const vrpx_env* env, void* stream) {
+  int rc = check_env(env, __func__);
+  if (rc) return rc;
+  if (env->kind != VRPX_IRP) return VRPX_OK;
+  VRPX_DEVICE_GUARD(env->xy);
+  k_refresh_mask<<<grid_for(env->B, 256), 256, 0, (cudaStream_t)stream>>>(*env);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
 int vrpx_env_set_visited(const vrpx_env* env, const double* visited, void* stream) {
   int rc = check_env(env, __func__);
   if (rc) return rc;
+  VRPX_DEVICE_GUARD(env->xy);
   VRPX_CHECK_ARG(visited, "visited must be non-NULL");
   k_set_visited<<<grid_for(env->B, 256), 256, 0, (cudaStream_t)stream>>>(*env, visited);
   VRPX_LAUNCH_CHECK();

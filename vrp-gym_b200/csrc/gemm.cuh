@@ -1,5 +1,5 @@
 // gemm.cuh — internal GEMM interface shared by the SIMT cross-check path (encoder.cu) and the
-// tcgen05 tensor-core paths (gemm_tc4.cu, gemm_tc3.cu).
+// tcgen05 tensor-core path (gemm_tc4.cu).
 #pragma once
 #include "common.cuh"
 
@@ -25,11 +25,14 @@ struct GemmArgs {
 int gemm_simt(const GemmArgs& a, cudaStream_t stream);     // fp32 FFMA, smem tiled (encoder.cu)
 int gemm_tc(const GemmArgs& a, cudaStream_t stream);       // production: tcgen05.mma kind::f16 on f16 hi/lo halves (≈fp32), persistent,
                                                            // TMA-staged, A operand in TMEM (gemm_tc4.cu)
-int gemm_tc_tf32(const GemmArgs& a, cudaStream_t stream);  // previous generation: kind::tf32 3-term split (gemm_tc3.cu), cross-check
 
-// path: 0 tcgen05 f16-split (production), 1 fp32 SIMT, 2 tcgen05 3xTF32
+// path: 0 tcgen05 f16-split (production), 1 fp32 SIMT (cross-check: separates tensor-core error from algorithmic error)
 inline int gemm_dispatch(int path, const GemmArgs& a, cudaStream_t stream) {
-  return path == 0 ? gemm_tc(a, stream) : (path == 2 ? gemm_tc_tf32(a, stream) : gemm_simt(a, stream));
+  if (path != 0 && path != 1) {
+    set_error("gemm path %d does not exist (0: tcgen05 f16-split, 1: fp32 SIMT)", path);
+    return VRPX_ERR_ARG;
+  }
+  return path == 0 ? gemm_tc(a, stream) : gemm_simt(a, stream);
 }
 
 }  // namespace vrpx

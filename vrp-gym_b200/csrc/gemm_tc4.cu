@@ -3,13 +3,13 @@
 //   Y[R][NOUT] = epilogue( X[R][K] · W[NOUT][K]^T ),  fp32 in / fp32 out.
 //
 // Precision policy: every fp32 operand is carried as two halves, hi = f16(x) and lo = f16(x - hi) (22 significant bits,
-// like the TF32 hi/lo pair of gemm_tc3.cu), and  D = Xlo·Whi + Xhi·Wlo + Xhi·Whi  accumulates in fp32 TMEM.  A kind::f16
+// like a TF32 hi/lo pair), and  D = Xlo·Whi + Xhi·Wlo + Xhi·Whi  accumulates in fp32 TMEM.  A kind::f16
 // MMA covers K = 16 per instruction at the issue rate of a kind::tf32 MMA with K = 8, and reads the same bytes of shared
 // memory per instruction: half the tensor time and half the operand traffic of 3xTF32.  W is scaled by 2^8 before the
 // split so that its lo halves stay in the normal f16 range (the epilogue multiplies by 2^-8); activations are O(1).
 // Operands must stay below 65504 / 2^8 (weights) and 65504 (activations) in magnitude.
 //
-// Pipeline (gemm_tc3.cu's, with 64-wide k blocks and no shared-memory rewriting):
+// Pipeline (64-wide k blocks, no shared-memory rewriting):
 //   k_split_w16  W -> Whi | Wlo (f16, [NOUT][K]) once per call (W is at most 512 x 512)
 //   warp 4      TMA producer: per stage two raw fp32 X boxes (32 floats x 128 rows) + the Whi and Wlo boxes (64 halves x
 //               128 rows), all SWIZZLE_128B
@@ -424,13 +424,20 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
   if ((rc = make_map(&mx, a.X, a.R, a.K, false))) return rc;
   if ((rc = make_map(&mwh, w16, a.NOUT, a.K, true))) return rc;
   if ((rc = make_map(&mwl, w16 + nw, a.NOUT, a.K, true))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  // the attribute is per device: once per device this process uses (a per-process flag left a second GPU without it)
+  static std::mutex attr_mu;
+  static bool attr_set[64] = {false};
+  {
+    int dev = 0;
+    VRPX_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(attr_mu);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   // grid = (CTAs per column tile) x (column tiles): a multiple of nct, see the tile loop of the kernel
   const int nct = a.NOUT / BN;
@@ -453,6 +460,8 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
 extern "C" int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float* W, int32_t NOUT,
                                const float* bias, int32_t relu, const float* residual, const float* scale,
                                const float* shift, float* Y, int32_t path, void* stream) {
+  VRPX_CHECK_ARG(X && W && Y && R >= 1, "NULL argument");
+  VRPX_DEVICE_GUARD(X);
   vrpx::GemmArgs g{X, R, K, W, NOUT, bias, relu, residual, scale, shift, Y};
   return vrpx::gemm_dispatch(path, g, (cudaStream_t)stream);
 }

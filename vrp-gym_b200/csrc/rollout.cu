@@ -659,6 +659,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
                  void* ws, int64_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(env && w && h && logp && cost && steps && ws, "NULL argument");
+  VRPX_DEVICE_GUARD(h);
   VRPX_CHECK_ARG(env->kind >= 0 && env->kind <= 2 && env->N >= 2 && env->N <= VRPX_MAX_NODES && env->B >= 1,
                  "bad env header");
   VRPX_CHECK_ARG(env->xy && env->depot && env->visited && env->mask && env->cur && env->load, "env arrays");
@@ -666,7 +667,9 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   VRPX_CHECK_ARG(mode >= 0 && mode <= 2, "bad mode");
   VRPX_CHECK_ARG(mode != VRPX_TEACHER || tape, "teacher mode needs a tape");
   VRPX_CHECK_ARG(Tmax >= 1 && Tmax <= 1000 && t_begin >= 0, "t_begin / Tmax out of range");
-  VRPX_CHECK_ARG(coupling >= 0, "coupling must be >= 0");
+  // attention row (b, head) reads the mask of instance quirk_row(b, head, G): it must stay inside the batch
+  VRPX_CHECK_ARG(coupling >= 0 && (coupling == 0 || (coupling <= env->B && env->B % coupling == 0)),
+                 "coupling group must be 0 or a divisor of the batch size");
   VRPX_CHECK_ARG(ws_bytes >= vrpx_rollout_workspace_bytes(env->B, env->N), "workspace too small");
   VRPX_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
   VRPX_CHECK_ARG(w->ag_t && w->al_t && w->a_c && w->a_q0 && w->m_t && w->m_c, "decoder weights");

@@ -133,6 +133,8 @@ class TSPEnv:
         """Re-upload if a caller edited instances through `sampler.graphs[i].nodes[n][...] = v`."""
         if not self._sampler_stale and self._sampler.version != self._uploaded_version:
             self._upload_instances()
+            # edited demands change the IRP rule `demand - load > 0` of the CURRENT state (no-op for TSP / VRP)
+            vrpx.check(vrpx.lib().vrpx_env_refresh_mask(C.byref(self._view()), vrpx.stream_ptr(self._device)))
 
     def _reset_episode(self):
         vrpx.check(vrpx.lib().vrpx_env_reset(C.byref(self._view()), vrpx.stream_ptr(self._device)))

@@ -25,16 +25,16 @@ class _Store:
         self.edges = [None] * num_graphs  # per graph: list of (source, target) marked as visited (drawing only)
         self.version = 0
 
-    def draw_graph(self, g: int):
-        """Sample instance g from the legacy global numpy stream in the reference's order
-        (vrp_graph.py:29 rand(N,2) -> :34 choice(N, depots, replace=False) -> :42 uniform(1,10,(N,1))/C)."""
-        n = self.xy.shape[1]
-        self.xy[g] = np.random.rand(n, 2)
-        self.depots[g] = np.random.choice(n, size=self.depots.shape[1], replace=False)
-        C = 0.2449 * n + 26.12  # vrp_graph.py:41
-        d = np.random.uniform(low=1, high=10, size=(n, 1)) / C
-        d[self.depots[g]] = 0
-        self.demand[g] = d[:, 0]
+    def draw_all(self):
+        """Sample every instance from the legacy global numpy stream in the reference's order — per graph
+        vrp_graph.py:29 rand(N,2) -> :34 choice(N, depots, replace=False) -> :42 uniform(1,10,(N,1))/C, one graph
+        after the other (vrp_network.py:41-42) — in ONE call into the C generator (csrc/mt19937_legacy.cu) that
+        continues numpy's global state, instead of three numpy calls per graph."""
+        from vrpx import legacy_stream
+
+        depots = np.empty(self.depots.shape, np.int64)
+        legacy_stream.draw_instances(self.xy.shape[0], self.xy.shape[1], self.depots.shape[1], out=(self.xy, depots, self.demand))
+        self.depots[:] = depots
 
 
 class _NodeAttrs:
@@ -124,7 +124,7 @@ class VRPGraph:
         self.offset = np.array([0, 0.065])
         if _store is None:
             _store = _Store(1, num_nodes, num_depots)
-            _store.draw_graph(0)
+            _store.draw_all()
             _index = 0
         self._s, self._g = _store, _index
 

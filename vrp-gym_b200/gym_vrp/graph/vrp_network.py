@@ -25,8 +25,7 @@ class VRPNetwork:
         self.plot_demand = plot_demand
         self._store = _Store(num_graphs, num_nodes, num_depots)
         if _sample:
-            for g in range(num_graphs):  # vrp_network.py:41-42 — one instance after the other
-                self._store.draw_graph(g)
+            self._store.draw_all()  # vrp_network.py:41-42 — one instance after the other, same stream order
         self.graphs: List[VRPGraph] = _GraphList(self)
 
     # ---- bulk accessors (vrp_network.py:80-108, :154-169): array views instead of per-graph loops

@@ -22,7 +22,7 @@ EMB = 128
 LAYERS = 3
 
 
-ABI_VERSION = 3  # must equal VRPX_ABI_VERSION of include/vrpx.h
+ABI_VERSION = 4  # must equal VRPX_ABI_VERSION of include/vrpx.h
 
 
 class VrpxError(RuntimeError):
@@ -107,6 +107,11 @@ def lib():
     L.vrpx_env_step.argtypes = [C.POINTER(EnvView), vp, vp, vp, vp, vp]
     L.vrpx_env_observe.argtypes = [C.POINTER(EnvView), vp, vp, vp, vp]
     L.vrpx_env_set_visited.argtypes = [C.POINTER(EnvView), vp, vp]
+    L.vrpx_env_refresh_mask.argtypes = [C.POINTER(EnvView), vp]
+    L.vrpx_mt19937_seed.argtypes = [C.c_uint32, vp, vp]
+    L.vrpx_mt19937_permutation_head.argtypes = [vp, vp, i64, i64, vp]
+    L.vrpx_mt19937_instances.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+    L.vrpx_mt19937_random_actions.argtypes = [vp, vp, vp, i64, i32, vp]
     L.vrpx_encoder_workspace_bytes.argtypes = [i64, i32]
     L.vrpx_encoder_workspace_bytes.restype = i64
     L.vrpx_encoder_forward.argtypes = [C.POINTER(EncoderWeights), C.POINTER(EnvView), vp, vp, i64, i32, i32,
