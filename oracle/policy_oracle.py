@@ -102,11 +102,14 @@ def decoder_logits(sd, h, mask, first, last, load=None, C=10.0, glimpse_mask=Non
     return u.masked_fill(mask.bool(), float("-inf"))  # :98
 
 
-def rollout(sd, env: EnvOracle, greedy=True, train=False, tape=None, return_trace=False):
+def rollout(sd, env: EnvOracle, greedy=True, train=False, tape=None, return_trace=False, dtype=torch.float32):
     """The rollout loop — graph_tsp_agent.py:61-92 / graph_vrp_agent.py:52-83 /
     graph_irp_agent.py:54-105.
 
     `tape` (T,B) int: teacher-forced actions (replayed instead of argmax / sampling).
+    `dtype`: float32 = the reference's arithmetic.  float64 (with a float64 `sd`) evaluates the SAME f32 weights on the
+    SAME f32-rounded observations (graph_tsp_agent.py:72 casts the state to f32) without rounding in between — the
+    yardstick that measures how far the reference's own fp32 result is from its exact value.
     Returns (acc_loss (B,), acc_log_prob (B,)[, trace dict]).
     """
     kind = env.kind
@@ -114,8 +117,8 @@ def rollout(sd, env: EnvOracle, greedy=True, train=False, tape=None, return_trac
     load = None
     if kind == IRP:
         st, load_np = st
-        load = torch.tensor(load_np, dtype=torch.float)
-    st = torch.tensor(st, dtype=torch.float)
+        load = torch.tensor(load_np, dtype=torch.float).to(dtype)
+    st = torch.tensor(st, dtype=torch.float).to(dtype)
     B, N = st.shape[:2]
     if kind == TSP:
         h = encoder_forward(sd, st[:, :, :2], None, train)
@@ -128,7 +131,7 @@ def rollout(sd, env: EnvOracle, greedy=True, train=False, tape=None, return_trac
     first = sd["decoder._first_node"].reshape(1, E).repeat(B, 1)
     last = sd["decoder._last_node"].reshape(1, E).repeat(B, 1)
     acc_loss = torch.zeros(B)
-    acc_logp = torch.zeros(B)
+    acc_logp = torch.zeros(B, dtype=dtype)
     trace = {"actions": [], "logits": [], "logp": [], "reward": []}
     done, t = False, 0
     while not done:
@@ -141,7 +144,7 @@ def rollout(sd, env: EnvOracle, greedy=True, train=False, tape=None, return_trac
         else:
             a = torch.distributions.Categorical(logits=u).sample()  # :105-106
         if greedy and tape is None:
-            logp = torch.zeros(B)  # :100
+            logp = torch.zeros(B, dtype=dtype)  # :100
         else:
             logp = u.gather(1, a[:, None])[:, 0] - torch.logsumexp(u, dim=-1)  # :107
         if not greedy:
@@ -153,8 +156,8 @@ def rollout(sd, env: EnvOracle, greedy=True, train=False, tape=None, return_trac
         acc_loss = acc_loss + torch.tensor(r, dtype=torch.float)  # f32 accumulate (:85)
         if kind == IRP:
             s2, load_np = s2
-            load = torch.tensor(load_np, dtype=torch.float)
-        st = torch.tensor(s2, dtype=torch.float)
+            load = torch.tensor(load_np, dtype=torch.float).to(dtype)
+        st = torch.tensor(s2, dtype=torch.float).to(dtype)
         if return_trace:
             trace["actions"].append(a.numpy().copy())
             trace["logits"].append(u.detach().numpy().copy())

@@ -1,6 +1,7 @@
 // common.cuh — shared helpers for libvrpx (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -36,6 +37,15 @@ void count_launch(int n = 1);
   } while (0)
 
 int num_sms();  // multiprocessor count of the current device (cached)
+
+// NVTX range around the host side of a phase (encoder / score tables / decode loop / backward): shows up in nsys / ncu
+// timelines; costs nothing when no tool is attached (header-only NVTX v3, lazily bound).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Every launching entry point runs on the device that OWNS its buffers, not on whatever device happens to be current
 // in the calling thread: the guard looks the owner of a device pointer up (cudaPointerGetAttributes), switches to it

@@ -757,6 +757,7 @@ int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, co
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(env && w && wb && h && tape && trace && qg && wts && g && ws, "NULL argument");
   VRPX_DEVICE_GUARD(h);
+  NvtxRange nvtx_range("vrpx:decoder_backward");
   // the glimpse mask of attention row (b, head) is read at quirk_row(): it must stay inside the batch
   VRPX_CHECK_ARG(coupling >= 0 && (coupling == 0 || (coupling <= env->B && env->B % coupling == 0)),
                  "coupling group must be 0 or a divisor of the batch size");

@@ -459,6 +459,7 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(w && h && ws, "weights / h / ws must be non-NULL");
   VRPX_DEVICE_GUARD(h);
+  NvtxRange nvtx_range(train ? "vrpx:encoder_forward(train)" : "vrpx:encoder_forward");
   VRPX_CHECK_ARG(!saved || train, "activations are only saved in train mode");
   VRPX_CHECK_ARG(B >= 1 && N >= 1 && N <= VRPX_MAX_NODES, "bad B or N");
   VRPX_CHECK_ARG(w->f == 2 || w->f == 3, "node feature count must be 2 or 3");

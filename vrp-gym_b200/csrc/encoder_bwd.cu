@@ -216,6 +216,7 @@ int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_encoder_weig
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(w && wt && saved && g && grads && ws, "NULL argument");
   VRPX_DEVICE_GUARD(g);
+  NvtxRange nvtx_range("vrpx:encoder_backward");
   VRPX_CHECK_ARG(B >= 1 && N >= 1 && N <= VRPX_MAX_NODES, "bad B or N");
   VRPX_CHECK_ARG(x || (env && env->xy && (w->f == 2 || env->demand)), "need x or an env with features");
   VRPX_CHECK_ARG(ws_bytes >= vrpx_encoder_backward_workspace_bytes(B, N), "workspace too small");

@@ -140,7 +140,13 @@ __global__ void k_split_w16(const float* __restrict__ W, __half* __restrict__ hi
   lo[i] = __float2half_rn(x - __half2float(h));
 }
 
-template <bool RES, bool GATE>
+// SPLITACC: the two cross terms (Xlo·Whi, Xhi·Wlo) accumulate in their own TMEM accumulator and are added to the main
+// Xhi·Whi sum by the epilogue in fp32.  The tensor core TRUNCATES when it adds a k16 step into the fp32 accumulator; with
+// one accumulator a K = 1024 contraction is a chain of 192 such additions at full magnitude (a one-sided ~3e-6 relative
+// error, which the decoder's 10·tanh pointer logits amplify to the 1e-5 parity bound); with the cross terms apart the
+// full-magnitude chain is 64 long and the other 128 additions happen at 2^-11 of the magnitude.  Costs the accumulator
+// double buffering (the epilogue of a tile no longer overlaps the MMAs of the next): used for K >= 1024 only.
+template <bool RES, bool GATE, bool SPLITACC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh,
            const __grid_constant__ CUtensorMap mapWl) {
@@ -220,10 +226,44 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     if (lane == 0) {
       uint32_t kbc = 0, ti = 0;
       for (int64_t rt = rt0; rt < nrt; rt += rts, ++ti) {
-        const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+        const uint32_t acc = SPLITACC ? 0u : (ti & 1), aph = SPLITACC ? (ti & 1) : ((ti >> 1) & 1);
         mbar_wait(smem_u32(&s_acc_free[acc]), aph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem + acc * BN;
+        const uint32_t d = tmem + acc * BN, dx = SPLITACC ? tmem + BN : d;   // main / cross-term accumulators
+        if (!SPLITACC && nkb == 2) {
+          // K = 128 (QKV, out-proj, FF1, the K = 128 backward products): both k blocks are resident (3 stages), so ALL
+          // cross terms are issued before the first main term.  The truncating accumulations of the 16 cross-term MMAs
+          // then happen while the accumulator holds only the 2^-11-sized cross sum; the full-magnitude chain is the 8
+          // main MMAs (measured bias of the result: -1.5e-7 instead of -3.8e-7 relative, like SPLITACC, at no TMEM cost).
+          const uint32_t s0 = kbc % STAGES, ph0 = (kbc / STAGES) & 1, s1 = (kbc + 1) % STAGES, ph1 = ((kbc + 1) / STAGES) & 1;
+          mbar_wait(smem_u32(&s_conv_done[s0]), ph0);
+          mbar_wait(smem_u32(&s_conv_done[s1]), ph1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sidx[2] = {s0, s1};
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              unsigned char* st = smem + sidx[kb] * STAGE_BYTES;
+              const uint32_t ah = tmem + TMEM_A0 + sidx[kb] * 64, alo = ah + 32;
+              const uint64_t wh = make_desc(smem_u32(st + 2 * TILE_BYTES)), wl = make_desc(smem_u32(st + 3 * TILE_BYTES));
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j) {
+                const uint64_t o = (uint64_t)(2 * j);
+                if (pass == 0) {
+                  mma_f16_ts(d, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u);
+                  mma_f16_ts(d, ah + 8 * j, wl + o, 1u);
+                } else {
+                  mma_f16_ts(d, ah + 8 * j, wh + o, 1u);
+                }
+              }
+            }
+          mma_commit(smem_u32(&s_stage_free[s0]));
+          mma_commit(smem_u32(&s_stage_free[s1]));
+          kbc += 2;
+          mma_commit(smem_u32(&s_acc_full[acc]));
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
           const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
           unsigned char* st = smem + s * STAGE_BYTES;
@@ -234,9 +274,9 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {   // k16 step: 8 TMEM columns of A, 32 bytes along the swizzled W rows
             const uint64_t o = (uint64_t)(2 * j);
-            mma_f16_ts(d, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u);
-            mma_f16_ts(d, ah + 8 * j, wl + o, 1u);
-            mma_f16_ts(d, ah + 8 * j, wh + o, 1u);
+            mma_f16_ts(dx, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u);
+            mma_f16_ts(dx, ah + 8 * j, wl + o, 1u);
+            mma_f16_ts(d, ah + 8 * j, wh + o, (SPLITACC && !(kb | j)) ? 0u : 1u);
           }
           mma_commit(smem_u32(&s_stage_free[s]));
         }
@@ -265,7 +305,7 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     }
     uint32_t ti = 0;
     for (int64_t rt = rt0; rt < nrt; rt += rts, ++ti) {
-      const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+      const uint32_t acc = SPLITACC ? 0u : (ti & 1), aph = SPLITACC ? (ti & 1) : ((ti >> 1) & 1);
       const int64_t row_base = rt * BM + q * 32;
       mbar_wait(smem_u32(&s_acc_full[acc]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -284,6 +324,19 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr)
             : "memory");
+        uint32_t w[SPLITACC ? 32 : 1];
+        if (SPLITACC) {   // the cross-term accumulator of the same chunk
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]),
+                "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
+                "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+              : "r"(taddr + BN)
+              : "memory");
+        }
         const int c = col0 + cc * 32 + lc * 4;   // this lane's 4 columns after the transpose
         // the (coalesced) residual / gate rows are fetched while the TMEM load is in flight
         float4 res[8], gt[8];
@@ -294,6 +347,10 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
           if (GATE) gt[i] = (r < a.R) ? *reinterpret_cast<const float4*>(a.gate + r * a.NOUT + c) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (SPLITACC) {   // main + cross terms, fp32 round-to-nearest
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[SPLITACC ? i : 0]));
+        }
         if (k == 1) {
           // both chunks are in registers: the accumulator can be refilled while this warp finishes its stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -400,6 +457,8 @@ static __half* split_scratch(cudaStream_t stream) {
 
 }  // namespace tc4
 
+static int g_force_split_acc = 0;   // vrpx_debug_gemm path 3: SPLITACC for every shape (A/B measurements)
+
 int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
   using namespace tc4;
   if (a.K % BK != 0 || a.NOUT % BN != 0 || a.R <= 0) {
@@ -432,10 +491,12 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
     VRPX_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(attr_mu);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -446,10 +507,13 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
   if (per_ct < 1) per_ct = 1;
   if (per_ct > nrt) per_ct = nrt;
   const int grid = (int)(per_ct * nct);
-  if (a.residual && a.gate) k_gemm_tc4<true, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else if (a.residual) k_gemm_tc4<true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else if (a.gate) k_gemm_tc4<false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else k_gemm_tc4<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  const bool split_acc = (g_force_split_acc ? g_force_split_acc > 0 : a.K >= 1024) && !a.gate;   // see SPLITACC
+  if (split_acc && a.residual) k_gemm_tc4<true, false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else if (split_acc) k_gemm_tc4<false, false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else if (a.residual && a.gate) k_gemm_tc4<true, true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else if (a.residual) k_gemm_tc4<true, false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else if (a.gate) k_gemm_tc4<false, true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  else k_gemm_tc4<false, false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }
@@ -463,5 +527,11 @@ extern "C" int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float
   VRPX_CHECK_ARG(X && W && Y && R >= 1, "NULL argument");
   VRPX_DEVICE_GUARD(X);
   vrpx::GemmArgs g{X, R, K, W, NOUT, bias, relu, residual, scale, shift, Y};
+  if (path == 3 || path == 4) {   // 3: tcgen05 with the split accumulator forced on, 4: forced off (A/B of SPLITACC)
+    vrpx::g_force_split_acc = (path == 3) ? 1 : -1;
+    const int rc = vrpx::gemm_tc(g, (cudaStream_t)stream);
+    vrpx::g_force_split_acc = 0;
+    return rc;
+  }
   return vrpx::gemm_dispatch(path, g, (cudaStream_t)stream);
 }

@@ -95,6 +95,19 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
     __syncthreads();
   }
 
+  // Snapshot of the decoder-visible masks for the glimpses of the first step (see RolloutParams::gmask), then a grid
+  // barrier: no instance may step before every CTA has taken its snapshot and finished its Q~g rows.
+  {
+    uint32_t* gm = p.gmask + (size_t)(p.t0 & 1) * B * 4;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t base = tile * RTM;
+      const int cnt = (int)((B - base < RTM) ? (B - base) : RTM);
+      if (tid < cnt * 4) gm[base * 4 + tid] = __ldcg(p.env.mask + base * 4 + tid);
+    }
+    bar_target += gridDim.x;
+    grid_barrier(p.bar, bar_target);
+  }
+
   // Table mode: the rows S1[b][last], S0[b] (, SL[b]) the NEXT tile will need are copied to shared memory with cp.async
   // while the current tile runs its pointer-logit phase, so the dependent chain cur -> table row -> softmax does not
   // sit exposed at the head of every tile.  One warp per instance, issued and consumed by the same warp.
@@ -126,6 +139,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
   for (; t < p.t0 + p.Tmax; ++t) {
     const int trel = t - p.t0;
     bool cta_unfinished = false;
+    const uint32_t* __restrict__ gm_rd = p.gmask + (size_t)(t & 1) * B * 4;   // masks BEFORE step t, every instance
+    uint32_t* __restrict__ gm_wr = p.gmask + (size_t)((t + 1) & 1) * B * 4;   // masks after step t
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t base = tile * RTM;
       const int cnt = (int)((B - base < RTM) ? (B - base) : RTM);
@@ -286,8 +301,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           // masks of the instances whose rows the reference adds to heads 2t and 2t+1 (mask.repeat(H,1), graph_decoder.py:93)
           uint32_t nb0[4], nb1[4];
           {
-            const uint32_t* m0 = p.env.mask + quirk_row(b, 2 * t, p.G) * 4;
-            const uint32_t* m1 = p.env.mask + quirk_row(b, 2 * t + 1, p.G) * 4;
+            const uint32_t* m0 = gm_rd + quirk_row(b, 2 * t, p.G) * 4;
+            const uint32_t* m1 = gm_rd + quirk_row(b, 2 * t + 1, p.G) * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) { nb0[i] = __ldcg(m0 + i); nb1[i] = __ldcg(m1 + i); }
           }
@@ -321,7 +336,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
           }
           const float lf = s_loadf[m];
           // lane j holds mask word (j & 3) of the instance whose mask the reference adds to head j >> 2
-          const uint32_t mword = __ldcg(p.env.mask + quirk_row(b, lane >> 2, p.G) * 4 + (lane & 3));
+          const uint32_t mword = __ldcg(gm_rd + quirk_row(b, lane >> 2, p.G) * 4 + (lane & 3));
 #pragma unroll
           for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
@@ -561,11 +576,17 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
         p.env.load[b] = load;
 #pragma unroll
         for (int i = 0; i < 4; ++i) p.env.visited[b * 4 + i] = v.w[i];
+        Bits128 dm = v;   // decoder-visible mask after this step
         if (kind == VRPX_IRP) {
           Bits128 x = demand_exceeds(dem, N, load);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) p.env.mask[b * 4 + i] = v.w[i] | x.w[i];
+          for (int i = 0; i < 4; ++i) {
+            dm.w[i] = v.w[i] | x.w[i];
+            p.env.mask[b * 4 + i] = dm.w[i];
+          }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gm_wr[b * 4 + i] = dm.w[i];
         // f32 accumulation of f32(reward) in step order (graph_tsp_agent.py:85); cost = -acc_loss
         p.cost[b] = (t == 0 ? 0.f : p.cost[b]) + (float)r.dist;
         if (p.mode != VRPX_GREEDY) p.logp[b] = (t == 0 ? 0.f : p.logp[b]) + s_lp[m];
@@ -622,14 +643,16 @@ float vrpx_debug_rollout_kernel_ms(void) {
   return ms;
 }
 
+// header | Q~g [B][1024] f32 | gmask [2][B][4] u32
+static inline int64_t rollout_gmask_offset(int64_t B) { return kRolloutHdr + B * (int64_t)QW * (int64_t)sizeof(float); }
 int64_t vrpx_rollout_workspace_bytes(int64_t B, int32_t N) {
   (void)N;
-  return kRolloutHdr + B * (int64_t)QW * (int64_t)sizeof(float);
+  return rollout_gmask_offset(B) + 2 * B * 4 * (int64_t)sizeof(uint32_t);
 }
 
 int64_t vrpx_rollout_workspace_qg_offset(void) { return kRolloutHdr; }
 
-// table-mode workspace: header | Q~g | S0 | SL (IRP) | S1 | QK slice | c | q^ | m_t^T, every segment 256-byte aligned
+// table-mode workspace: header | Q~g | gmask | S0 | SL (IRP) | S1 | QK slice | c | q^ | m_t^T, every segment 256-byte aligned
 namespace {
 struct TableLayout {
   int64_t s0, sl, s1, qk, cbuf, qhat, mnt, total;
@@ -638,7 +661,7 @@ inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 TableLayout table_layout(int kind, int64_t B, int N) {
   TableLayout L;
   const int64_t f = (int64_t)sizeof(float);
-  L.s0 = align256(kRolloutHdr + B * QW * f);
+  L.s0 = align256(vrpx_rollout_workspace_bytes(B, N));
   L.sl = align256(L.s0 + B * NH * N * f);
   L.s1 = (kind == VRPX_IRP) ? align256(L.sl + B * NH * N * f) : L.sl;
   L.qk = align256(L.s1 + B * N * NH * N * f);
@@ -660,6 +683,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   cudaStream_t stream = (cudaStream_t)stream_;
   VRPX_CHECK_ARG(env && w && h && logp && cost && steps && ws, "NULL argument");
   VRPX_DEVICE_GUARD(h);
+  NvtxRange nvtx_range("vrpx:rollout");
   VRPX_CHECK_ARG(env->kind >= 0 && env->kind <= 2 && env->N >= 2 && env->N <= VRPX_MAX_NODES && env->B >= 1,
                  "bad env header");
   VRPX_CHECK_ARG(env->xy && env->depot && env->visited && env->mask && env->cur && env->load, "env arrays");
@@ -697,6 +721,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   p.bar = reinterpret_cast<unsigned*>(ws);
   p.notdone = reinterpret_cast<int*>(ws) + 8;
   p.qg = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kRolloutHdr);
+  p.gmask = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + rollout_gmask_offset(env->B));
   p.m16 = reinterpret_cast<const uint2*>(reinterpret_cast<char*>(ws) + kRolloutSmall);
   p.s1 = nullptr;
   p.s0 = p.sl = nullptr;
@@ -708,7 +733,11 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
     if (ws_bytes >= L.total && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
       char* base = reinterpret_cast<char*>(ws);
       float* s1 = reinterpret_cast<float*>(base + L.s1);
-      int rc = build_score_table(h, w->qk_w, env->B, env->N, reinterpret_cast<float*>(base + L.qk), s1, stream);
+      int rc;
+      {
+        NvtxRange nvtx_tables("vrpx:score_tables");
+        rc = build_score_table(h, w->qk_w, env->B, env->N, reinterpret_cast<float*>(base + L.qk), s1, stream);
+      }
       if (rc) return rc;
       p.s1 = s1;
       p.s0 = reinterpret_cast<float*>(base + L.s0);
@@ -752,6 +781,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
     }
     VRPX_CUDA(cudaEventRecord(g_ev0, stream));
   }
+  NvtxRange nvtx_decode("vrpx:decode_loop");
   VRPX_CUDA(cudaLaunchCooperativeKernel((void*)k_rollout, dim3(grid), dim3(NT), args, smem_total, stream));
   count_launch();
   if (split) {

@@ -23,6 +23,9 @@ struct RolloutParams {
   float* qg0;         // optional copy of Q~g before the `first` fold (backward)
   uint32_t* mask_hist;  // optional [Tmax][B][4] decoder-visible mask before each step (backward)
   float* load_hist;   // optional [Tmax][B] f32 vehicle load before each step (backward)
+  uint32_t* gmask;    // [2][B][4] persistent kernel only: the decoder-visible masks every glimpse of step t reads are the
+                      // snapshot gmask[t & 1] (the env transition of step t writes gmask[(t + 1) & 1]); reading env.mask in
+                      // place would race with the transitions of tiles that are already past their pointer phase
   unsigned* bar;      // grid barrier counter
   int* notdone;       // [Tmax + 1]
   long long* prof;    // optional [8] cycle counters per phase (debug, vrpx_debug_rollout_profile)

@@ -233,6 +233,7 @@ class TSPEnv:
     def generate_mask(self):
         """(batch, nodes) f64 of 0/1: 1 = node cannot be visited next (tsp.py:131-148).  The rules are applied
         on the device after every transition, so this only materialises the current mask."""
+        self._sync_instances()
         out = torch.empty((self.batch_size, self.num_nodes), dtype=torch.float64, device=self._device)
         vrpx.check(vrpx.lib().vrpx_env_observe(C.byref(self._view()), None, vrpx.ptr(out), None,
                                                vrpx.stream_ptr(self._device)))
