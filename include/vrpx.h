@@ -307,6 +307,16 @@ VRPX_API int vrpx_debug_gemm(const float* X, int64_t R, int32_t K, const float* 
                              int32_t relu, const float* residual, const float* scale, const float* shift, float* Y,
                              int32_t path, void* stream);
 
+/* Test / measurement hooks of the fused encoder feed-forward kernel (csrc/ff_fused.cu):
+ *   vrpx_debug_ff_fused          Y = (residual + relu(X·W1^T + b1)·W2^T + b2) * scale + shift, X/Y/residual [R][128],
+ *                                W1 [512][128], W2 [128][512] (graph_encoder.py:177-181,196); scale/shift may be NULL
+ *   vrpx_debug_encoder_fuse_ff   1 (default): vrpx_encoder_forward runs the FF block through that kernel whenever no
+ *                                activations are saved for a backward pass; 0: two GEMMs (A/B measurements) */
+VRPX_API int vrpx_debug_ff_fused(const float* X, int64_t R, const float* W1, const float* b1, const float* W2,
+                                 const float* b2, const float* residual, const float* scale, const float* shift, float* Y,
+                                 void* stream);
+VRPX_API void vrpx_debug_encoder_fuse_ff(int32_t enable);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 VRPX_API int64_t vrpx_launch_count(void);
 

@@ -92,3 +92,38 @@ def test_gemm_tn_accumulate(R, M, N):
     ref = C0.double() + A.double().T @ Bm.double()
     err = (C.double() - ref).abs().max().item()
     assert err <= 2e-5 * ref.abs().max().item() + 1e-5, (R, M, N, err)
+
+
+@pytest.mark.parametrize("R", [128, 1000, 5, 19000, 148 * 128 * 2 + 77])
+@pytest.mark.parametrize("affine", [True, False], ids=["bn_affine", "plain"])
+def test_ff_fused_kernel(R, affine):
+    """csrc/ff_fused.cu: Y = (residual + relu(X W1^T + b1) W2^T + b2) * scale + shift in one tcgen05 kernel (the hidden
+    activation stays in tensor memory) against float64; in place (Y aliases X and the residual) like the encoder calls it."""
+    import vrpx
+
+    dev = vrpx.require_device()
+    g = torch.Generator(device="cpu").manual_seed(R)
+    X = torch.randn(R, 128, generator=g).to(dev)
+    W1 = (torch.randn(512, 128, generator=g) / 128 ** 0.5).to(dev)
+    b1 = (torch.randn(512, generator=g) * 0.1).to(dev)
+    W2 = (torch.randn(128, 512, generator=g) / 512 ** 0.5).to(dev)
+    b2 = (torch.randn(128, generator=g) * 0.1).to(dev)
+    sc = (torch.rand(128, generator=g) + 0.5).to(dev) if affine else None
+    sh = torch.randn(128, generator=g).to(dev) if affine else None
+    ref = X.double() + torch.relu(X.double() @ W1.double().T + b1.double()) @ W2.double().T + b2.double()
+    if affine:
+        ref = ref * sc.double() + sh.double()
+    Y = X.clone()
+    vrpx.check(vrpx.lib().vrpx_debug_ff_fused(vrpx.ptr(Y), R, vrpx.ptr(W1), vrpx.ptr(b1), vrpx.ptr(W2), vrpx.ptr(b2), vrpx.ptr(Y),
+                                              vrpx.ptr(sc) if affine else None, vrpx.ptr(sh) if affine else None, vrpx.ptr(Y),
+                                              vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    err = (Y.double() - ref).abs().max().item()
+    assert err <= 1e-5 * max(ref.abs().max().item(), 1.0), (R, affine, err)
+    # out of place, a second call on the same stream (scratch reuse)
+    Y2 = torch.empty_like(X)
+    vrpx.check(vrpx.lib().vrpx_debug_ff_fused(vrpx.ptr(X), R, vrpx.ptr(W1), vrpx.ptr(b1), vrpx.ptr(W2), vrpx.ptr(b2), vrpx.ptr(X),
+                                              vrpx.ptr(sc) if affine else None, vrpx.ptr(sh) if affine else None, vrpx.ptr(Y2),
+                                              vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(Y, Y2)

@@ -445,7 +445,18 @@ constexpr int64_t kSavedStatFloats = 2 * VRPX_LAYERS * 2 * 128;                 
 
 using namespace vrpx;
 
+static int g_fuse_ff = 1;   // vrpx_debug_encoder_fuse_ff
+
 extern "C" {
+
+void vrpx_debug_encoder_fuse_ff(int32_t enable) { g_fuse_ff = enable; }
+
+int vrpx_debug_ff_fused(const float* X, int64_t R, const float* W1, const float* b1, const float* W2, const float* b2,
+                        const float* residual, const float* scale, const float* shift, float* Y, void* stream) {
+  VRPX_CHECK_ARG(X && Y, "NULL argument");
+  VRPX_DEVICE_GUARD(X);
+  return ff_fused(X, R, W1, b1, W2, b2, residual, scale, shift, Y, (cudaStream_t)stream);
+}
 
 int64_t vrpx_encoder_workspace_bytes(int64_t B, int32_t N) { return kSmallWs + B * (int64_t)N * kRowBytes; }
 
@@ -541,14 +552,25 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
         k_affine<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(y1, s1, R * 32, h1);
         VRPX_LAUNCH_CHECK();
       }
-      GemmArgs g3{h1, R, E, L.ff0_w, FF, L.ff0_b, 1, nullptr, nullptr, nullptr, hid};
-      if ((rc = gemm(g3, stream))) return rc;
+      const bool fuse_ff = gemm_path == 0 && !saved && g_fuse_ff;   // the hidden tile stays on chip (ff_fused.cu)
+      if (fuse_ff) {
+        if (!train) {
+          if ((rc = ff_fused(h1, R, L.ff0_w, L.ff0_b, L.ff2_w, L.ff2_b, h1, s2->scale, s2->shift, hc, stream))) return rc;
+          continue;
+        }
+        if ((rc = ff_fused(h1, R, L.ff0_w, L.ff0_b, L.ff2_w, L.ff2_b, h1, nullptr, nullptr, y2, stream))) return rc;
+      } else {
+        GemmArgs g3{h1, R, E, L.ff0_w, FF, L.ff0_b, 1, nullptr, nullptr, nullptr, hid};
+        if ((rc = gemm(g3, stream))) return rc;
+      }
       if (!train) {
         GemmArgs g4{hid, R, FF, L.ff2_w, E, L.ff2_b, 0, hc, s2->scale, s2->shift, hc};
         if ((rc = gemm(g4, stream))) return rc;
       } else {
-        GemmArgs g4{hid, R, FF, L.ff2_w, E, L.ff2_b, 0, h1, nullptr, nullptr, y2};
-        if ((rc = gemm(g4, stream))) return rc;
+        if (!fuse_ff) {
+          GemmArgs g4{hid, R, FF, L.ff2_w, E, L.ff2_b, 0, h1, nullptr, nullptr, y2};
+          if ((rc = gemm(g4, stream))) return rc;
+        }
         k_bn_stats<<<num_sms() * 4, 256, 0, stream>>>(y2, R, s2);
         VRPX_LAUNCH_CHECK();
         k_bn_fold<<<1, E, 0, stream>>>(s2, L.bn2_w, L.bn2_b, L.bn2_mean, L.bn2_var, 1, R,

@@ -26,6 +26,10 @@ int gemm_simt(const GemmArgs& a, cudaStream_t stream);     // fp32 FFMA, smem ti
 int gemm_tc(const GemmArgs& a, cudaStream_t stream);       // production: tcgen05.mma kind::f16 on f16 hi/lo halves (≈fp32), persistent,
                                                            // TMA-staged, A operand in TMEM (gemm_tc4.cu)
 
+// the encoder feed-forward block in one kernel (ff_fused.cu): Y = (residual + relu(X·W1^T + b1)·W2^T + b2) * scale + shift
+int ff_fused(const float* X, int64_t R, const float* W1, const float* b1, const float* W2, const float* b2,
+             const float* residual, const float* scale, const float* shift, float* Y, cudaStream_t stream);
+
 // path: 0 tcgen05 f16-split (production), 1 fp32 SIMT (cross-check: separates tensor-core error from algorithmic error)
 inline int gemm_dispatch(int path, const GemmArgs& a, cudaStream_t stream) {
   if (path != 0 && path != 1) {

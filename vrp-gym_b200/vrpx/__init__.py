@@ -147,6 +147,9 @@ def lib():
     L.vrpx_rollout.argtypes = [C.POINTER(EnvView), C.POINTER(DecoderWeights), vp, i32, i64, u64, u64, vp, i32, i32,
                                vp, vp, vp, vp, C.POINTER(RolloutTrace), vp, i64, vp]
     L.vrpx_debug_gemm.argtypes = [vp, i64, i32, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp]
+    L.vrpx_debug_ff_fused.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.vrpx_debug_encoder_fuse_ff.argtypes = [i32]
+    L.vrpx_debug_encoder_fuse_ff.restype = None
     if L.vrpx_abi_version() != ABI_VERSION:
         raise VrpxError("libvrpx.so ABI version mismatch")
     _lib = L
