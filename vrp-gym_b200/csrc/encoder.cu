@@ -446,10 +446,14 @@ constexpr int64_t kSavedStatFloats = 2 * VRPX_LAYERS * 2 * 128;                 
 using namespace vrpx;
 
 static int g_fuse_ff = 1;   // vrpx_debug_encoder_fuse_ff
+namespace vrpx { extern int g_ff_dbg; }
 
 extern "C" {
 
-void vrpx_debug_encoder_fuse_ff(int32_t enable) { g_fuse_ff = enable; }
+void vrpx_debug_encoder_fuse_ff(int32_t enable) {
+  g_fuse_ff = enable & 1;
+  vrpx::g_ff_dbg = enable >> 1;   // bits above 0: measurement switches of the kernel (ff_fused.cu, Args::dbg)
+}
 
 int vrpx_debug_ff_fused(const float* X, int64_t R, const float* W1, const float* b1, const float* W2, const float* b2,
                         const float* residual, const float* scale, const float* shift, float* Y, void* stream) {

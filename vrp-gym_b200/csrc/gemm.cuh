@@ -1,6 +1,9 @@
 // gemm.cuh — internal GEMM interface shared by the SIMT cross-check path (encoder.cu) and the
 // tcgen05 tensor-core path (gemm_tc4.cu).
 #pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace vrpx {
@@ -21,6 +24,15 @@ struct GemmArgs {
   float* Y;
   const float* gate = nullptr;  // [R][NOUT] or nullptr: ReLU-backward gate (acc is zeroed where gate <= 0)
 };
+
+// a prepared tcgen05 GEMM (gemm_tc4.cu): tensor maps + launch shape, reusable while the buffers stay where they are
+struct GemmPlan {
+  GemmArgs a;
+  CUtensorMap mx, mwh, mwl;
+  int grid, variant;
+};
+int gemm_tc_plan(const GemmArgs& a, __half* w16, GemmPlan* plan, cudaStream_t stream);   // w16: 2 * NOUT * K halves
+int gemm_tc_launch(const GemmPlan& plan, cudaStream_t stream);
 
 int gemm_simt(const GemmArgs& a, cudaStream_t stream);     // fp32 FFMA, smem tiled (encoder.cu)
 int gemm_tc(const GemmArgs& a, cudaStream_t stream);       // production: tcgen05.mma kind::f16 on f16 hi/lo halves (≈fp32), persistent,

@@ -332,30 +332,25 @@ int split_weights(const float* W, __half* w16, int n, cudaStream_t stream) {
 
 static int g_force_split_acc = 0;   // vrpx_debug_gemm path 3: SPLITACC for every shape (A/B measurements)
 
-int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
+// Prepare a GEMM once (validate, split W into `w16` = hi | lo halves, encode the three tensor maps, pick the grid and the
+// kernel variant) and launch it any number of times: the decode loop runs the same GEMM-B on the same buffers at every
+// step, so the weight split and the map encodes happen once per rollout instead of once per step.
+int gemm_tc_plan(const GemmArgs& a, __half* w16, GemmPlan* pl, cudaStream_t stream) {
   using namespace tc4;
   if (a.K % BK != 0 || a.NOUT % BN != 0 || a.R <= 0) {
     set_error("gemm_tc: unsupported shape R=%lld K=%d NOUT=%d", (long long)a.R, a.K, a.NOUT);
     return VRPX_ERR_ARG;
   }
-  if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) {
+  if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15) || (reinterpret_cast<uintptr_t>(w16) & 15)) {
     set_error("gemm_tc: operands must be 16-byte aligned");
     return VRPX_ERR_ARG;
   }
   const int nw = a.NOUT * a.K;
-  if (nw > kMaxSplitWeights) {
-    set_error("gemm_tc: weight matrix too large for the split scratch (%d x %d)", a.NOUT, a.K);
-    return VRPX_ERR_ARG;
-  }
-  __half* w16 = split_scratch(stream);
-  if (!w16) return VRPX_ERR_CUDA;
-  k_split_w16<<<(nw + 255) / 256, 256, 0, stream>>>(a.W, w16, w16 + nw, nw);
-  VRPX_LAUNCH_CHECK();
-  CUtensorMap mx, mwh, mwl;
   int rc;
-  if ((rc = make_map(&mx, a.X, a.R, a.K, false))) return rc;
-  if ((rc = make_map(&mwh, w16, a.NOUT, a.K, true))) return rc;
-  if ((rc = make_map(&mwl, w16 + nw, a.NOUT, a.K, true))) return rc;
+  if ((rc = split_weights(a.W, w16, nw, stream))) return rc;
+  if ((rc = make_map(&pl->mx, a.X, a.R, a.K, false))) return rc;
+  if ((rc = make_map(&pl->mwh, w16, a.NOUT, a.K, true))) return rc;
+  if ((rc = make_map(&pl->mwl, w16 + nw, a.NOUT, a.K, true))) return rc;
   // the attribute is per device: once per device this process uses (a per-process flag left a second GPU without it)
   static std::mutex attr_mu;
   static bool attr_set[64] = {false};
@@ -379,16 +374,39 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path
   int64_t per_ct = num_sms() / nct;
   if (per_ct < 1) per_ct = 1;
   if (per_ct > nrt) per_ct = nrt;
-  const int grid = (int)(per_ct * nct);
+  pl->a = a;
+  pl->grid = (int)(per_ct * nct);
   const bool split_acc = (g_force_split_acc ? g_force_split_acc > 0 : a.K >= 1024) && !a.gate;   // see SPLITACC
-  if (split_acc && a.residual) k_gemm_tc4<true, false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else if (split_acc) k_gemm_tc4<false, false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else if (a.residual && a.gate) k_gemm_tc4<true, true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else if (a.residual) k_gemm_tc4<true, false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else if (a.gate) k_gemm_tc4<false, true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
-  else k_gemm_tc4<false, false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, mx, mwh, mwl);
+  pl->variant = split_acc ? (a.residual ? 5 : 4) : ((a.residual ? 1 : 0) | (a.gate ? 2 : 0));
+  return VRPX_OK;
+}
+
+int gemm_tc_launch(const GemmPlan& pl, cudaStream_t stream) {
+  using namespace tc4;
+  const GemmArgs& a = pl.a;
+  switch (pl.variant) {
+    case 5: k_gemm_tc4<true, false, true><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
+    case 4: k_gemm_tc4<false, false, true><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
+    case 3: k_gemm_tc4<true, true, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
+    case 2: k_gemm_tc4<false, true, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
+    case 1: k_gemm_tc4<true, false, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
+    default: k_gemm_tc4<false, false, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
+  }
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
+}
+
+int gemm_tc(const GemmArgs& a, cudaStream_t stream) {  // production path: plan + launch on the per-stream scratch
+  if ((int64_t)a.NOUT * a.K > tc4::kMaxSplitWeights) {
+    set_error("gemm_tc: weight matrix too large for the split scratch (%d x %d)", a.NOUT, a.K);
+    return VRPX_ERR_ARG;
+  }
+  __half* w16 = tc4::split_scratch(stream);
+  if (!w16) return VRPX_ERR_CUDA;
+  GemmPlan pl;
+  int rc = gemm_tc_plan(a, w16, &pl, stream);
+  if (rc) return rc;
+  return gemm_tc_launch(pl, stream);
 }
 
 }  // namespace vrpx

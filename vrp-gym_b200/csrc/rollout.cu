@@ -655,7 +655,7 @@ int64_t vrpx_rollout_workspace_qg_offset(void) { return kRolloutHdr; }
 // table-mode workspace: header | Q~g | gmask | S0 | SL (IRP) | S1 | QK slice | c | q^ | m_t^T, every segment 256-byte aligned
 namespace {
 struct TableLayout {
-  int64_t s0, sl, s1, qk, cbuf, qhat, mnt, total;
+  int64_t s0, sl, s1, qk, cbuf, qhat, mnt, agn, afn, w16b, total;
 };
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 TableLayout table_layout(int kind, int64_t B, int N) {
@@ -669,7 +669,10 @@ TableLayout table_layout(int kind, int64_t B, int N) {
   L.cbuf = align256(L.qk + score_table_slice(B) * N * 768 * f);
   L.qhat = align256(L.cbuf + B * QW * f);
   L.mnt = align256(L.qhat + B * E * f);
-  L.total = align256(L.mnt + (int64_t)QW * E * f);
+  L.agn = align256(L.mnt + (int64_t)QW * E * f);
+  L.afn = align256(L.agn + (int64_t)QW * E * f);
+  L.w16b = align256(L.afn + (int64_t)QW * E * f);
+  L.total = align256(L.w16b + (int64_t)2 * QW * E * 2);
   return L;
 }
 }  // namespace
@@ -726,7 +729,7 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   p.s1 = nullptr;
   p.s0 = p.sl = nullptr;
   p.cbuf = p.qhat = nullptr;
-  float* m_nt = nullptr;
+  SplitWorkspace sw{nullptr, nullptr, nullptr, nullptr};
   // table mode: whole-episode call with the large workspace and the rank-48 factors
   if (w->qk_w && t_begin == 0 && Tmax >= 3) {
     const TableLayout L = table_layout(env->kind, env->B, env->N);
@@ -744,16 +747,20 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
       p.sl = reinterpret_cast<float*>(base + L.sl);
       p.cbuf = reinterpret_cast<float*>(base + L.cbuf);
       p.qhat = reinterpret_cast<float*>(base + L.qhat);
-      m_nt = reinterpret_cast<float*>(base + L.mnt);
+      sw.m_nt = reinterpret_cast<float*>(base + L.mnt);
+      sw.ag_n = reinterpret_cast<float*>(base + L.agn);
+      sw.af_n = reinterpret_cast<float*>(base + L.afn);
+      sw.w16b = reinterpret_cast<__half*>(base + L.w16b);
     }
   }
-  // Split-step mode: the persistent kernel runs steps 0 and 1 (classic phases, they build Q~g and S0), every later step
-  // is three launches over the whole batch (rollout_steps.cu)
+  // Split-step mode (default for whole-episode table-mode calls): every step is a handful of launches over the whole
+  // batch (rollout_steps.cu); the persistent kernel below serves the classic mode, resumed single-step calls and the
+  // all-persistent A/B switch
   const bool split = p.s1 != nullptr && g_split_steps;
+  GemmPlan plan_b;
   if (split) {
-    int rc = prepare_split_weights(w->m_t, m_nt, stream);
+    int rc = prepare_split_weights(p, sw, &plan_b, stream);
     if (rc) return rc;
-    p.Tmax = 2;
   }
   // shared-memory staging of the table rows: as many segments as fit beside the GEMM buffers
   p.tb_segs = 0;
@@ -768,6 +775,24 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   VRPX_CHECK_ARG((int64_t)(Tmax + 1 + 8) * 4 <= kRolloutSmall, "Tmax too large for workspace header");
 
   VRPX_CUDA(cudaMemsetAsync(ws, 0, kRolloutSmall, stream));
+  if (split) {
+    if (g_time_kernel) {
+      if (!g_ev0) {
+        VRPX_CUDA(cudaEventCreate(&g_ev0));
+        VRPX_CUDA(cudaEventCreate(&g_ev1));
+      }
+      VRPX_CUDA(cudaEventRecord(g_ev0, stream));
+    }
+    NvtxRange nvtx_decode("vrpx:decode_loop");
+    int rc = run_first_steps(p, sw, plan_b, stream);
+    if (rc) return rc;
+    if ((rc = run_split_steps(p, t_begin + 2, plan_b, stream))) return rc;   // also writes the step count
+    if (g_time_kernel) {
+      VRPX_CUDA(cudaEventRecord(g_ev1, stream));
+      g_ev_valid = true;
+    }
+    return VRPX_OK;
+  }
   k_split_m16<<<(QW / 2) * E / 256, 256, 0, stream>>>(w->m_t, reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + kRolloutSmall));
   VRPX_LAUNCH_CHECK();
   VRPX_CUDA(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
@@ -784,11 +809,6 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
   NvtxRange nvtx_decode("vrpx:decode_loop");
   VRPX_CUDA(cudaLaunchCooperativeKernel((void*)k_rollout, dim3(grid), dim3(NT), args, smem_total, stream));
   count_launch();
-  if (split) {
-    p.Tmax = Tmax;
-    int rc = run_split_steps(p, t_begin + 2, m_nt, stream);
-    if (rc) return rc;
-  }
   if (g_time_kernel) {
     VRPX_CUDA(cudaEventRecord(g_ev1, stream));
     g_ev_valid = true;

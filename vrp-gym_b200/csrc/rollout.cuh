@@ -1,6 +1,7 @@
 // rollout.cuh — parameter block shared by the persistent rollout kernel (rollout.cu) and the split-step kernels
 // (rollout_steps.cu).
 #pragma once
+#include "gemm.cuh"
 #include "tile_gemm.cuh"
 
 namespace vrpx {
@@ -40,9 +41,18 @@ struct RolloutParams {
   int tb_segs;        // table rows staged in shared memory per instance: 0 none, 1 = S1, 2 = S1 + S0, 3 = S1 + S0 + SL
 };
 
-// rollout_steps.cu: decode steps [t_first, t0 + Tmax) as three launches per step (glimpse, batched GEMM-B, pointer) and
-// the final step count; m_nt = m_t transposed ([128][1024], built by prepare_split_weights).
-int prepare_split_weights(const float* m_t, float* m_nt, cudaStream_t stream);
-int run_split_steps(const RolloutParams& p, int t_first, const float* m_nt, cudaStream_t stream);
+// rollout_steps.cu: a whole-episode table-mode rollout as launches over the whole batch — steps 0 and 1 (run_first_steps:
+// they build Q~g and S0), then three launches per step (run_split_steps: glimpse, batched GEMM-B, pointer) and the final
+// step count.  SplitWorkspace: transposed copies of the folded weights for the tcgen05 GEMMs ([NOUT][K] layout) and the
+// split halves of m_t^T, in the rollout workspace.
+struct SplitWorkspace {
+  float* m_nt;     // [128][1024]  m_t^T
+  float* ag_n;     // [1024][128]  ag_t^T
+  float* af_n;     // [1024][128]  af_t^T (TSP / VRP)
+  __half* w16b;    // 2 x [128][1024] halves: hi | lo of m_t^T * 2^8
+};
+int prepare_split_weights(const RolloutParams& p, const SplitWorkspace& w, GemmPlan* plan_b, cudaStream_t stream);
+int run_first_steps(const RolloutParams& p, const SplitWorkspace& w, const GemmPlan& plan_b, cudaStream_t stream);
+int run_split_steps(const RolloutParams& p, int t_first, const GemmPlan& plan_b, cudaStream_t stream);
 
 }  // namespace vrpx

@@ -380,6 +380,272 @@ __global__ void __launch_bounds__(SW * 32) k_step_pointer(const RolloutParams p,
   if (tid == 0 && s_anyleft) atomicAdd(p.notdone + trel, 1);
 }
 
+
+// ---------------------------------------------------------------- steps 0 and 1 in split form
+// The first two steps have no table row yet: step 0 runs on the learned placeholders (q~ = Q~g + a_q0, graph_decoder.py:79-81),
+// step 1 completes the per-episode tables (Q~g += A_f h[first]; S0 = Q~g_head · h_n; IRP: SL = a_load_head · h_n).  They
+// used to run inside the persistent kernel (4.7 ms at C4, L2-bound on 16-instance tiles); here they are whole-batch
+// launches like every later step: a mean / gather kernel, a batched tcgen05 GEMM for the 128 -> 1024 query fold, and a
+// glimpse kernel that computes the scores from q~ itself (one warp per instance, mma.sync TF32 3-term, the score and value
+// passes of the persistent kernel's phase P2) instead of reading them from the tables.
+
+// G[b] = mean_n h[b, n]  (graph_decoder.py:75-77), one warp per instance
+__global__ void __launch_bounds__(256) k_episode_mean(const float* __restrict__ h, int64_t B, int N, float* __restrict__ G) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n = 0; n < N; ++n) {   // same summation order as the persistent kernel's prologue
+    const float4 v = __ldg(hp + n * (E / 4));
+    g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+  }
+  const float inv = 1.0f / (float)N;
+  reinterpret_cast<float4*>(G + b * E)[lane] = make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv);
+}
+
+// Xf[b] = h[b, cur[b]]: the first chosen node after step 0 (graph_decoder.py:108-113)
+__global__ void __launch_bounds__(256) k_gather_cur(const float* __restrict__ h, const int* __restrict__ cur, int64_t B, int N,
+                                                    float* __restrict__ Xf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int c = __ldcg(cur + b);
+  reinterpret_cast<float4*>(Xf + b * E)[lane] = __ldg(reinterpret_cast<const float4*>(h + (b * N + c) * E) + lane);
+}
+
+// dst[c][r] = src[r][c]
+__global__ void k_transpose(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  dst[(size_t)c * rows + r] = src[i];
+}
+
+// S[node][head] = h[node][:] · q[head][:] on the tensor pipe (m16n8k8 TF32 3-term; M = 16 nodes, N = 8 heads), q = 8 x 128
+// floats in shared memory.  Fragment coordinates g = lane >> 2, tq = lane & 3; the K (embedding) axis is permuted so that
+// every thread streams whole float4 chunks (see the persistent kernel).  store(n, which, v): node n, head 2 tq + which.
+template <class Store>
+__device__ __forceinline__ void warp_glimpse_scores(const float* q, const float4* __restrict__ hrow, int N, int lane, Store&& store) {
+  const int g = lane >> 2, tq = lane & 3;
+  float4 qv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) qv[c] = *reinterpret_cast<const float4*>(q + g * E + 16 * c + 4 * tq);
+  __syncwarp();
+  for (int n0 = 0; n0 < N; n0 += 16) {
+    const int na = n0 + g, nbb = n0 + g + 8;
+    float acc6[2][3][4];
+#pragma unroll
+    for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+      for (int b_ = 0; b_ < 3; ++b_)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc6[a_][b_][i] = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = half * 4 + cc;
+        va[cc] = (na < N) ? __ldg(hrow + na * (E / 4) + 4 * c + tq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[cc] = (nbb < N) ? __ldg(hrow + nbb * (E / 4) + 4 * c + tq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = half * 4 + cc;
+        const float ae[4] = {va[cc].x, va[cc].y, va[cc].z, va[cc].w};
+        const float be[4] = {vb[cc].x, vb[cc].y, vb[cc].z, vb[cc].w};
+        const float qe[4] = {qv[c].x, qv[c].y, qv[c].z, qv[c].w};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+          split_tf32(ae[2 * u], ah[0], al[0]);
+          split_tf32(be[2 * u], ah[1], al[1]);
+          split_tf32(ae[2 * u + 1], ah[2], al[2]);
+          split_tf32(be[2 * u + 1], ah[3], al[3]);
+          split_tf32(qe[2 * u], bh0, bl0);
+          split_tf32(qe[2 * u + 1], bh1, bl1);
+          mma_tf32_16x8x8(acc6[u][0], al, bh0, bh1);
+          mma_tf32_16x8x8(acc6[u][1], ah, bl0, bl1);
+          mma_tf32_16x8x8(acc6[u][2], ah, bh0, bh1);
+        }
+      }
+    }
+    float acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      acc[i] = ((acc6[0][0][i] + acc6[1][0][i]) + (acc6[0][1][i] + acc6[1][1][i])) + (acc6[0][2][i] + acc6[1][2][i]);
+    if (na < N) { store(na, 0, acc[0]); store(na, 1, acc[1]); }
+    if (nbb < N) { store(nbb, 0, acc[2]); store(nbb, 1, acc[3]); }
+  }
+}
+
+constexpr int FW = 8;   // warps (= instances) per CTA of the first-step glimpse kernel
+__global__ void __launch_bounds__(FW * 32) k_step_glimpse_first(const RolloutParams p, int t) {
+  __shared__ __align__(16) float s_slot[FW][QW];
+  const int trel = t - p.t0;
+  if (episode_over(p, trel)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.env.N, kind = p.env.kind;
+  const int64_t B = p.env.B, b = (int64_t)blockIdx.x * FW + warp;
+  if (b >= B) return;
+  float* slot = s_slot[warp];
+  const int g = lane >> 2, tq = lane & 3;
+  const float4* hrow = reinterpret_cast<const float4*>(p.h + b * N * E);
+  const float lf = (float)p.env.load[b];
+  if (p.mask_hist && lane < 4) p.mask_hist[((int64_t)trel * B + b) * 4 + lane] = __ldcg(p.env.mask + b * 4 + lane);
+  if (p.load_hist && lane == 0) p.load_hist[(int64_t)trel * B + b] = lf;
+  // ---- q~: step 0 = Q~g + a_q0 (+ load · a_load); step 1 = the finished Q~g (its scores are S0, kept for every later step)
+  {
+    const float4* qg4 = reinterpret_cast<const float4*>(p.qg + b * QW);
+    for (int i = lane; i < QW / 4; i += 32) {
+      float4 q = __ldcg(qg4 + i);
+      if (t == 0) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.w.a_q0) + i);
+        q.x += a0.x; q.y += a0.y; q.z += a0.z; q.w += a0.w;
+        if (kind == VRPX_IRP) {
+          const float4 al = __ldg(reinterpret_cast<const float4*>(p.w.a_load) + i);
+          q.x = fmaf(lf, al.x, q.x); q.y = fmaf(lf, al.y, q.y); q.z = fmaf(lf, al.z, q.z); q.w = fmaf(lf, al.w, q.w);
+        }
+      }
+      *reinterpret_cast<float4*>(slot + 4 * i) = q;
+    }
+  }
+  __syncwarp();
+  float* s0 = (t == 1) ? p.s0 + (size_t)b * NH * N : nullptr;
+  warp_glimpse_scores(slot, hrow, N, lane, [&](int n, int which, float v) {
+    slot[(2 * tq + which) * E + n] = v;
+    if (s0) s0[(2 * tq + which) * N + n] = v;
+  });
+  __syncwarp();
+  float pr[NH][4];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = lane + 32 * i;
+      pr[hh][i] = (n < N) ? slot[hh * E + n] : -INFINITY;
+    }
+  __syncwarp();
+  if (t == 1) {
+    if (kind == VRPX_IRP) {   // SL = a_load_head · h_n, and its share of this step's scores
+      for (int i = lane; i < QW / 4; i += 32)
+        *reinterpret_cast<float4*>(slot + 4 * i) = __ldg(reinterpret_cast<const float4*>(p.w.a_load) + i);
+      __syncwarp();
+      float* sl = p.sl + (size_t)b * NH * N;
+      warp_glimpse_scores(slot, hrow, N, lane, [&](int n, int which, float v) {
+        slot[(2 * tq + which) * E + n] = v;
+        sl[(2 * tq + which) * N + n] = v;
+      });
+      __syncwarp();
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = lane + 32 * i;
+          if (n < N) pr[hh][i] = fmaf(lf, slot[hh * E + n], pr[hh][i]);
+        }
+      __syncwarp();
+    }
+    // + the table row of the node chosen at step 0: (A_l h[last])_head · h_n
+    const int last = __ldcg(p.env.cur + b);
+    const float* r1 = p.s1 + (((size_t)b * N + last) * NH) * N;
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = lane + 32 * i;
+        if (n < N) pr[hh][i] += __ldg(r1 + hh * N + n);
+      }
+  }
+  // ---- scrambled additive mask (graph_decoder.py:93-94): lane j holds word (j & 3) of the mask added to head j >> 2
+  {
+    const uint32_t mword = __ldcg(p.env.mask + quirk_row(b, lane >> 2, p.G) * 4 + (lane & 3));
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t wsel = __shfl_sync(0xffffffffu, mword, hh * 4 + i);
+        pr[hh][i] += (float)((wsel >> lane) & 1u);   // -inf stays -inf for the lanes beyond N
+      }
+  }
+  // ---- softmax per head over nodes (lane = node, 4 strides cover N <= 128)
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mx = fmaxf(mx, pr[hh][i]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = lane + 32 * i;
+      pr[hh][i] = (n < N) ? expf(pr[hh][i] - mx) : 0.f;
+      sum += pr[hh][i];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[hh][i] *= inv;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = lane + 32 * i;
+    if (n < N) {
+      *reinterpret_cast<float4*>(slot + n * 8) = make_float4(pr[0][i], pr[1][i], pr[2][i], pr[3][i]);
+      *reinterpret_cast<float4*>(slot + n * 8 + 4) = make_float4(pr[4][i], pr[5][i], pr[6][i], pr[7][i]);
+    }
+  }
+  __syncwarp();
+  // ---- c[head][dim] = sum_n P[n][head] h_n[dim] (M = 16 dims, N = 8 heads, K = 8 nodes; the second pass over the
+  // instance's embeddings comes from L2)
+  float cacc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cacc[j][i] = 0.f;
+  for (int n0 = 0; n0 < N; n0 += 8) {
+    const int na = n0 + tq, nbb = n0 + tq + 4;
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int cq = 0; cq < 4; ++cq) {
+      va[cq] = (na < N) ? __ldg(hrow + na * (E / 4) + 8 * cq + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vb[cq] = (nbb < N) ? __ldg(hrow + nbb * (E / 4) + 8 * cq + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t bh0, bl0, bh1, bl1;
+    split_tf32((na < N) ? slot[na * 8 + g] : 0.f, bh0, bl0);
+    split_tf32((nbb < N) ? slot[nbb * 8 + g] : 0.f, bh1, bl1);
+#pragma unroll
+    for (int cq = 0; cq < 4; ++cq) {
+      const float ae[4] = {va[cq].x, va[cq].y, va[cq].z, va[cq].w};
+      const float be[4] = {vb[cq].x, vb[cq].y, vb[cq].z, vb[cq].w};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint32_t ah[4], al[4];
+        split_tf32(ae[2 * u], ah[0], al[0]);
+        split_tf32(ae[2 * u + 1], ah[1], al[1]);
+        split_tf32(be[2 * u], ah[2], al[2]);
+        split_tf32(be[2 * u + 1], ah[3], al[3]);
+        mma_tf32_16x8x8(cacc[2 * cq + u], al, bh0, bh1);
+        mma_tf32_16x8x8(cacc[2 * cq + u], ah, bl0, bl1);
+        mma_tf32_16x8x8(cacc[2 * cq + u], ah, bh0, bh1);
+      }
+    }
+  }
+  __syncwarp();   // every lane is done reading P before c is staged in the slot
+#pragma unroll
+  for (int cq = 0; cq < 4; ++cq)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int d = 32 * cq + 4 * g + 2 * u, j = 2 * cq + u;
+      *reinterpret_cast<float2*>(slot + (2 * tq) * E + d) = make_float2(cacc[j][0], cacc[j][2]);
+      *reinterpret_cast<float2*>(slot + (2 * tq + 1) * E + d) = make_float2(cacc[j][1], cacc[j][3]);
+    }
+  __syncwarp();
+  float4* dst = reinterpret_cast<float4*>(p.cbuf + b * QW);
+  for (int i = lane; i < QW / 4; i += 32) dst[i] = *reinterpret_cast<const float4*>(slot + 4 * i);
+}
+
 // steps executed = first step at whose start nobody was unfinished (it still runs, like the reference's loop), else Tmax
 __global__ void k_rollout_finish(const int* __restrict__ notdone, int t0, int Tmax, int* __restrict__ steps) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -396,24 +662,71 @@ __global__ void k_transpose_m(const float* __restrict__ m_t, float* __restrict__
   m_nt[n * QW + k] = m_t[i];
 }
 
-int prepare_split_weights(const float* m_t, float* m_nt, cudaStream_t stream) {
-  k_transpose_m<<<QW * E / 256, 256, 0, stream>>>(m_t, m_nt);
+int prepare_split_weights(const RolloutParams& p, const SplitWorkspace& w, GemmPlan* plan_b, cudaStream_t stream) {
+  k_transpose_m<<<QW * E / 256, 256, 0, stream>>>(p.w.m_t, w.m_nt);
+  VRPX_LAUNCH_CHECK();
+  k_transpose<<<QW * E / 256, 256, 0, stream>>>(p.w.ag_t, E, QW, w.ag_n);
+  VRPX_LAUNCH_CHECK();
+  if (p.w.af_t) {
+    k_transpose<<<QW * E / 256, 256, 0, stream>>>(p.w.af_t, E, QW, w.af_n);
+    VRPX_LAUNCH_CHECK();
+  }
+  // GEMM-B runs on the same buffers at every step: split m_t^T and encode its tensor maps once per rollout
+  GemmArgs ga{p.cbuf, p.env.B, QW, w.m_nt, E, p.w.m_c, 0, nullptr, nullptr, nullptr, p.qhat};
+  return gemm_tc_plan(ga, w.w16b, plan_b, stream);
+}
+
+static unsigned glimpse_launch_shape(int N, int64_t B, int* warps, size_t* smem) {
+  int gw = G_CTA_SMEM / glimpse_warp_bytes(N);
+  if (gw > GW_MAX) gw = GW_MAX;
+  *warps = gw;
+  *smem = (size_t)gw * glimpse_warp_bytes(N);
+  return (unsigned)((B + gw - 1) / gw);
+}
+
+// steps 0 and 1 of a whole-episode table-mode rollout (p.t0 == 0)
+int run_first_steps(const RolloutParams& p, const SplitWorkspace& w, const GemmPlan& plan_b, cudaStream_t stream) {
+  const int64_t B = p.env.B;
+  const int N = p.env.N;
+  const unsigned g8 = (unsigned)((B + 7) / 8), grid_p = (unsigned)((B + SW - 1) / SW), grid_f = (unsigned)((B + FW - 1) / FW);
+  int rc;
+  // ---- step 0: Q~g = A_g · mean_n h + a_c (the graph part of the folded query), then the placeholder step
+  k_episode_mean<<<g8, 256, 0, stream>>>(p.h, B, N, p.qhat);
+  VRPX_LAUNCH_CHECK();
+  GemmArgs g0{p.qhat, B, E, w.ag_n, QW, p.w.a_c, 0, nullptr, nullptr, nullptr, p.qg};
+  if ((rc = gemm_tc(g0, stream))) return rc;
+  if (p.qg0) VRPX_CUDA(cudaMemcpyAsync(p.qg0, p.qg, (size_t)B * QW * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  k_step_glimpse_first<<<grid_f, FW * 32, 0, stream>>>(p, 0);
+  VRPX_LAUNCH_CHECK();
+  if ((rc = gemm_tc_launch(plan_b, stream))) return rc;
+  k_step_pointer<<<grid_p, SW * 32, 0, stream>>>(p, 0);
+  VRPX_LAUNCH_CHECK();
+  if (p.Tmax < 2) return VRPX_OK;
+  // ---- step 1: fold the first chosen node into Q~g (graph_decoder.py:111-113; IRP has no `first` term), build S0 (, SL)
+  if (p.env.kind != VRPX_IRP) {
+    k_gather_cur<<<g8, 256, 0, stream>>>(p.h, p.env.cur, B, N, p.qhat);
+    VRPX_LAUNCH_CHECK();
+    GemmArgs g1{p.qhat, B, E, w.af_n, QW, nullptr, 0, p.qg, nullptr, nullptr, p.qg};
+    if ((rc = gemm_tc(g1, stream))) return rc;
+  }
+  k_step_glimpse_first<<<grid_f, FW * 32, 0, stream>>>(p, 1);
+  VRPX_LAUNCH_CHECK();
+  if ((rc = gemm_tc_launch(plan_b, stream))) return rc;
+  k_step_pointer<<<grid_p, SW * 32, 0, stream>>>(p, 1);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }
 
-int run_split_steps(const RolloutParams& p, int t_first, const float* m_nt, cudaStream_t stream) {
+int run_split_steps(const RolloutParams& p, int t_first, const GemmPlan& plan_b, cudaStream_t stream) {
   const int64_t B = p.env.B;
-  int gw = G_CTA_SMEM / glimpse_warp_bytes(p.env.N);
-  if (gw > GW_MAX) gw = GW_MAX;
-  const unsigned grid = (unsigned)((B + SW - 1) / SW), ggrid = (unsigned)((B + gw - 1) / gw);
-  const size_t smem = (size_t)gw * glimpse_warp_bytes(p.env.N);
+  int gw;
+  size_t smem;
+  const unsigned ggrid = glimpse_launch_shape(p.env.N, B, &gw, &smem), grid = (unsigned)((B + SW - 1) / SW);
   VRPX_CUDA(cudaFuncSetAttribute(k_step_glimpse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int t = t_first; t < p.t0 + p.Tmax; ++t) {
     k_step_glimpse<<<ggrid, gw * 32, smem, stream>>>(p, t);
     VRPX_LAUNCH_CHECK();
-    GemmArgs ga{p.cbuf, B, QW, m_nt, E, p.w.m_c, 0, nullptr, nullptr, nullptr, p.qhat};
-    int rc = gemm_tc(ga, stream);
+    int rc = gemm_tc_launch(plan_b, stream);
     if (rc) return rc;
     k_step_pointer<<<grid, SW * 32, 0, stream>>>(p, t);
     VRPX_LAUNCH_CHECK();
