@@ -62,7 +62,8 @@ struct Args {
   const float* scale;     // [128] or nullptr
   const float* shift;     // [128] or nullptr
   float* Y;               // [R][128]
-  int dbg;                // measurement switches (vrpx_debug_ff_fused_flags): bit 0 = chunk converters skip their arithmetic, bit 1 = no weight TMA after the first fill of the rings
+  int dbg;                // measurement switches (vrpx_debug_ff_fused_flags): bit 0 = chunk converters skip their arithmetic, bit 1 = no weight TMA after the first fill of the rings, bit 2 = converters skip their TMEM loads / stores,
+                          // bit 3 = the MMA thread does not wait for the converters (wrong results, shows the issue-bound time)
 };
 
 #define VRPX_TMEM_LD32(v, taddr)                                                                                          \
@@ -191,12 +192,12 @@ k_ff_fused(const Args a, const __grid_constant__ CUtensorMap mapX, const __grid_
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // the WHOLE warp runs the issue loop (converged); one elected lane issues each instruction (tc_common.cuh)
       uint32_t cc = 0, ti = 0;   // chunk counter (both products advance it in lock step), tile counter
       auto ff1 = [&](uint32_t c) {   // D1 = X · W1c^T, cross terms first
         const uint32_t s = c & 1, ph = (c >> 1) & 1;
         mbar_wait(smem_u32(&s_w1_full[s]), ph);
-        mbar_wait(smem_u32(&s_d1_free), (c & 1) ^ 1);
+        if (!(a.dbg & 8)) mbar_wait(smem_u32(&s_d1_free), (c & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem + TM_D1, xh = tmem + TM_XA, xl = tmem + TM_XA + 64;
         unsigned char* wb = smem + SM_W1 + s * W1_SLOT;
@@ -208,15 +209,15 @@ k_ff_fused(const Args a, const __grid_constant__ CUtensorMap mapX, const __grid_
           for (int jj = 0; jj < 4; ++jj) {
             const uint64_t o = (uint64_t)(2 * jj);
             const uint32_t ka = 8 * (4 * kh + jj);          // 8 packed TMEM columns per k16 step
-            mma_f16_ts(d, xl + ka, wh[kh] + o, (kh | jj) ? 1u : 0u, IDESC1);
-            mma_f16_ts(d, xh + ka, wl[kh] + o, 1u, IDESC1);
+            mma_f16_ts_w(d, xl + ka, wh[kh] + o, (kh | jj) ? 1u : 0u, IDESC1);
+            mma_f16_ts_w(d, xh + ka, wl[kh] + o, 1u, IDESC1);
           }
 #pragma unroll
         for (int kh = 0; kh < 2; ++kh)
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) mma_f16_ts(d, xh + 8 * (4 * kh + jj), wh[kh] + (uint64_t)(2 * jj), 1u, IDESC1);
-        mma_commit(smem_u32(&s_w1_free[s]));
-        mma_commit(smem_u32(&s_d1_full));
+          for (int jj = 0; jj < 4; ++jj) mma_f16_ts_w(d, xh + 8 * (4 * kh + jj), wh[kh] + (uint64_t)(2 * jj), 1u, IDESC1);
+        mma_commit_w(smem_u32(&s_w1_free[s]));
+        mma_commit_w(smem_u32(&s_d1_full));
       };
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
         mbar_wait(smem_u32(&s_xa_full), ti & 1);
@@ -225,12 +226,12 @@ k_ff_fused(const Args a, const __grid_constant__ CUtensorMap mapX, const __grid_
         for (int j = 0; j < NCH; ++j, ++cc) {
           if (j + 1 < NCH) {
             ff1(cc + 1);
-            if (j + 2 == NCH) mma_commit(smem_u32(&s_xa_free));   // every FF1 product of the tile has been issued
+            if (j + 2 == NCH) mma_commit_w(smem_u32(&s_xa_free));   // every FF1 product of the tile has been issued
           }
           // FF2(j): D2 += H_j · W2c^T, main and cross terms in separate accumulators
           const uint32_t s = cc & 1, ph = (cc >> 1) & 1;
           mbar_wait(smem_u32(&s_w2_full[s]), ph);
-          mbar_wait(smem_u32(&s_ha_full), cc & 1);
+          if (!(a.dbg & 8)) mbar_wait(smem_u32(&s_ha_full), cc & 1);
           if (j == 0) mbar_wait(smem_u32(&s_d2_free), (ti & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t ah = tmem + TM_HA, al = ah + 32;
@@ -240,14 +241,14 @@ k_ff_fused(const Args a, const __grid_constant__ CUtensorMap mapX, const __grid_
           for (int jj = 0; jj < 4; ++jj) {
             const uint64_t o = (uint64_t)(2 * jj);
             const uint32_t accum = (j | jj) ? 1u : 0u;
-            mma_f16_ts(tmem + TM_D2X, al + 8 * jj, wh + o, accum, IDESC2);
-            mma_f16_ts(tmem + TM_D2X, ah + 8 * jj, wl + o, 1u, IDESC2);
-            mma_f16_ts(tmem + TM_D2M, ah + 8 * jj, wh + o, accum, IDESC2);
+            mma_f16_ts_w(tmem + TM_D2X, al + 8 * jj, wh + o, accum, IDESC2);
+            mma_f16_ts_w(tmem + TM_D2X, ah + 8 * jj, wl + o, 1u, IDESC2);
+            mma_f16_ts_w(tmem + TM_D2M, ah + 8 * jj, wh + o, accum, IDESC2);
           }
-          mma_commit(smem_u32(&s_w2_free[s]));
-          mma_commit(smem_u32(&s_ha_free));
+          mma_commit_w(smem_u32(&s_w2_free[s]));
+          mma_commit_w(smem_u32(&s_ha_free));
         }
-        mma_commit(smem_u32(&s_d2_full));
+        mma_commit_w(smem_u32(&s_d2_full));
       }
     }
   } else if (warp < 8) {
@@ -260,8 +261,13 @@ k_ff_fused(const Args a, const __grid_constant__ CUtensorMap mapX, const __grid_
         mbar_wait(smem_u32(&s_d1_full), cc & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v0[32];
-        VRPX_TMEM_LD32(v0, tmem + lane_base + TM_D1 + hf * 32);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!(a.dbg & 4)) {
+          VRPX_TMEM_LD32(v0, tmem + lane_base + TM_D1 + hf * 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v0[c] = 0x3c003c00u;
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_d1_free));         // the next FF1 may overwrite D1
@@ -284,9 +290,11 @@ k_ff_fused(const Args a, const __grid_constant__ CUtensorMap mapX, const __grid_
         mbar_wait(smem_u32(&s_ha_free), (cc & 1) ^ 1);            // FF2 of the previous chunk has consumed HA
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t ha = tmem + lane_base + TM_HA + hf * 16;   // packed: 16 columns per 32 hidden values
-        tmem_st16(ha, hi);
-        tmem_st16(ha + 32, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (!(a.dbg & 4)) {
+          tmem_st16(ha, hi);
+          tmem_st16(ha + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_ha_full));

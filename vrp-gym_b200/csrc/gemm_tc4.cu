@@ -151,7 +151,7 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // the WHOLE warp runs the issue loop (converged); one elected lane issues each instruction (tc_common.cuh)
       uint32_t kbc = 0, ti = 0;
       for (int64_t rt = rt0; rt < nrt; rt += rts, ++ti) {
         const uint32_t acc = SPLITACC ? 0u : (ti & 1), aph = SPLITACC ? (ti & 1) : ((ti >> 1) & 1);
@@ -179,17 +179,17 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
               for (int j = 0; j < BK / 16; ++j) {
                 const uint64_t o = (uint64_t)(2 * j);
                 if (pass == 0) {
-                  mma_f16_ts(d, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u, IDESC);
-                  mma_f16_ts(d, ah + 8 * j, wl + o, 1u, IDESC);
+                  mma_f16_ts_w(d, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u, IDESC);
+                  mma_f16_ts_w(d, ah + 8 * j, wl + o, 1u, IDESC);
                 } else {
-                  mma_f16_ts(d, ah + 8 * j, wh + o, 1u, IDESC);
+                  mma_f16_ts_w(d, ah + 8 * j, wh + o, 1u, IDESC);
                 }
               }
             }
-          mma_commit(smem_u32(&s_stage_free[s0]));
-          mma_commit(smem_u32(&s_stage_free[s1]));
+          mma_commit_w(smem_u32(&s_stage_free[s0]));
+          mma_commit_w(smem_u32(&s_stage_free[s1]));
           kbc += 2;
-          mma_commit(smem_u32(&s_acc_full[acc]));
+          mma_commit_w(smem_u32(&s_acc_full[acc]));
           continue;
         }
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
@@ -202,13 +202,13 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {   // k16 step: 8 TMEM columns of A, 32 bytes along the swizzled W rows
             const uint64_t o = (uint64_t)(2 * j);
-            mma_f16_ts(dx, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u, IDESC);
-            mma_f16_ts(dx, ah + 8 * j, wl + o, 1u, IDESC);
-            mma_f16_ts(d, ah + 8 * j, wh + o, (SPLITACC && !(kb | j)) ? 0u : 1u, IDESC);
+            mma_f16_ts_w(dx, alo + 8 * j, wh + o, (kb | j) ? 1u : 0u, IDESC);
+            mma_f16_ts_w(dx, ah + 8 * j, wl + o, 1u, IDESC);
+            mma_f16_ts_w(d, ah + 8 * j, wh + o, (SPLITACC && !(kb | j)) ? 0u : 1u, IDESC);
           }
-          mma_commit(smem_u32(&s_stage_free[s]));
+          mma_commit_w(smem_u32(&s_stage_free[s]));
         }
-        mma_commit(smem_u32(&s_acc_full[acc]));
+        mma_commit_w(smem_u32(&s_acc_full[acc]));
       }
     }
   } else if (warp >= 8) {

@@ -72,6 +72,29 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-collective variants: EVERY lane of a converged warp executes the call, one elected lane issues the instruction.
+// Issued from inside an `if (lane == 0)` region the compiler cannot prove the operands warp-uniform and wraps each
+// UTCHMMA in an ELECT / R2UR / BRA.U.ANY loop (~8 dependent instructions, 40-60 clocks per MMA): a kernel whose MMAs take
+// 32-64 clocks each then runs at half the tensor rate, bound by the issuing thread (measured: ff_fused.cu, 49 % tensor
+// active).  With the whole warp converged the descriptor arithmetic stays in uniform registers and the MMA is one
+// predicated instruction.
+__device__ __forceinline__ void mma_f16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
+      : "memory");
+}
+
 // kind::f16 instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
