@@ -22,6 +22,7 @@ namespace vrpx {
 
 int64_t score_table_slice(int64_t B);
 int build_score_table(const float* h, const float* qk_w, int64_t B, int N, float* qk_buf, float* s1, cudaStream_t stream);
+int build_score_table_fused(const float* h, const float* qk_w, int64_t B, int N, __half* w16, float* s1, cudaStream_t stream);
 
 // Rollout tile: RMT x 16 instances.  With 16 instances per tile the working set that has to survive in L2 between the
 // glimpse passes and the pointer-logit pass (all CTAs x tile x 25.6 KB) halves to 60 MB.
@@ -612,7 +613,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(const RolloutParams p) {
 }
 
 static long long* g_rollout_prof = nullptr;
-static int g_split_steps = 1;                        // vrpx_debug_rollout_split
+static int g_split_steps = 1;                        // vrpx_debug_rollout_split (bit 0)
+static int g_fused_tables = 1;                       // vrpx_debug_rollout_split (bit 1 clear = fused score-table kernel)
 static int g_time_kernel = 0;                        // vrpx_debug_rollout_timing
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static bool g_ev_valid = false;
@@ -629,7 +631,10 @@ extern "C" {
 /* Debug hook: device buffer of 8 x int64 that accumulates per-phase cycles of thread 0 of every CTA (NULL disables). */
 void vrpx_debug_rollout_profile(long long* dev_counters) { g_rollout_prof = dev_counters; }
 
-void vrpx_debug_rollout_split(int32_t enable) { g_split_steps = enable; }
+void vrpx_debug_rollout_split(int32_t enable) {
+  g_split_steps = enable & 1;
+  g_fused_tables = (enable & 2) ? 0 : 1;   // bit 1: build the score table with the two-kernel form (A/B measurements)
+}
 
 void vrpx_debug_rollout_timing(int32_t enable) {
   g_time_kernel = enable;
@@ -655,7 +660,7 @@ int64_t vrpx_rollout_workspace_qg_offset(void) { return kRolloutHdr; }
 // table-mode workspace: header | Q~g | gmask | S0 | SL (IRP) | S1 | QK slice | c | q^ | m_t^T, every segment 256-byte aligned
 namespace {
 struct TableLayout {
-  int64_t s0, sl, s1, qk, cbuf, qhat, mnt, agn, afn, w16b, total;
+  int64_t s0, sl, s1, qk, cbuf, qhat, mnt, agn, afn, w16b, qkw16, total;
 };
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 TableLayout table_layout(int kind, int64_t B, int N) {
@@ -672,7 +677,8 @@ TableLayout table_layout(int kind, int64_t B, int N) {
   L.agn = align256(L.mnt + (int64_t)QW * E * f);
   L.afn = align256(L.agn + (int64_t)QW * E * f);
   L.w16b = align256(L.afn + (int64_t)QW * E * f);
-  L.total = align256(L.w16b + (int64_t)2 * QW * E * 2);
+  L.qkw16 = align256(L.w16b + (int64_t)2 * QW * E * 2);
+  L.total = align256(L.qkw16 + (int64_t)2 * 768 * E * 2);
   return L;
 }
 }  // namespace
@@ -739,7 +745,10 @@ int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, const float
       int rc;
       {
         NvtxRange nvtx_tables("vrpx:score_tables");
-        rc = build_score_table(h, w->qk_w, env->B, env->N, reinterpret_cast<float*>(base + L.qk), s1, stream);
+        if (g_fused_tables)   // projection + table in one kernel (score_table_fused.cu); the two-kernel form is the A/B switch
+          rc = build_score_table_fused(h, w->qk_w, env->B, env->N, reinterpret_cast<__half*>(base + L.qkw16), s1, stream);
+        else
+          rc = build_score_table(h, w->qk_w, env->B, env->N, reinterpret_cast<float*>(base + L.qk), s1, stream);
       }
       if (rc) return rc;
       p.s1 = s1;
