@@ -260,8 +260,11 @@ VRPX_API int vrpx_rollout(const vrpx_env* env, const vrpx_decoder_weights* w, co
  *   vrpx_debug_rollout_kernel_ms  waits for the last bracketed launch and returns its duration (-1 if none) */
 VRPX_API void vrpx_debug_rollout_profile(long long* dev_counters);
 VRPX_API void vrpx_debug_rollout_timing(int32_t enable);
-/* Table mode runs the decode steps t >= 2 as three launches per step over the whole batch (default, enable = 1) or
- * keeps every step inside the persistent kernel (enable = 0; cross-check and A/B measurements). */
+/* A/B switches of the whole-episode table-mode rollout (default 1):
+ *   bit 0  set: every decode step is a handful of launches over the whole batch (rollout_steps.cu);
+ *          clear: every step inside the persistent kernel (cross-check and A/B measurements)
+ *   bit 1  set: build the score table with the two-kernel form (tcgen05 GEMM + k_score_table) instead of the fused kernel;
+ *   (programmatic dependent launch of the step kernels was measured and removed: 36.38 vs 36.36 ms per decode loop) */
 VRPX_API void vrpx_debug_rollout_split(int32_t enable);
 VRPX_API float vrpx_debug_rollout_kernel_ms(void);
 

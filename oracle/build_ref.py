@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Make the UNMODIFIED reference runnable on the GPU box: copy its two Python packages (agents/, gym_vrp/ — the whole
-hot path) from /root/reference into oracle/_ref/.
+hot path) and its own test files (tests/, run verbatim against this repo's packages by
+tests/test_gpu_reference_suite.py) from /root/reference into oracle/_ref/.
 
 TEST / BASELINE INFRASTRUCTURE ONLY.  oracle/_ref/ is git-ignored (the reference's sources never enter this repo's
 history) but not gpurun-ignored, so the copy travels to the GPU box like a built .so, where `bench.py --impl reference`
@@ -19,7 +20,7 @@ OUT = os.path.join(HERE, "_ref")
 def build(verbose=False):
     if not os.path.isdir(os.path.join(REF, "agents")):
         return os.path.isdir(os.path.join(OUT, "agents"))  # GPU box: use the copy that travelled, if any
-    for pkg in ("agents", "gym_vrp"):
+    for pkg in ("agents", "gym_vrp", "tests"):
         dst = os.path.join(OUT, pkg)
         if os.path.isdir(dst):
             shutil.rmtree(dst)

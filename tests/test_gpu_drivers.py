@@ -40,3 +40,37 @@ def test_training_checkpoint_roundtrip(tmp_path):
     a = agent.evaluate(deepcopy(env2))
     b = other.evaluate(deepcopy(env2))
     assert torch.allclose(a, b)
+
+
+@pytest.mark.parametrize("kind", ["tsp", "vrp"])
+def test_training_cost_curve_tracks_reference(golden_dir, kind):
+    """SURVEY §8f-2 (train_models.py:4-21): the same training run — Env(20, B=256, seed=123), Agent(seed=123),
+    `agent.train` — on the CUDA path, against the cost curve the UNMODIFIED reference logged on CPU for its first epochs
+    (tests/golden/ckpt_<kind>_20_123_eval.npz `train_log`, written by make_checkpoints.py; columns Epoch, Loss, Cost,
+    Advantage, Time as graph_tsp_agent.py:196-206).  Instances are identical (same numpy stream); the sampled actions are
+    not (Philox vs torch.multinomial), so the curves agree statistically: the smoothed cost follows the reference's within
+    6 % and falls as far."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "vrp-gym_b200"))
+    from agents import TSPAgent, VRPAgent
+    from gym_vrp.envs import TSPEnv, VRPEnv
+
+    ref = np.load(os.path.join(golden_dir, f"ckpt_{kind}_20_123_eval.npz"))["train_log"]
+    Env, Agent = {"tsp": (TSPEnv, TSPAgent), "vrp": (VRPEnv, VRPAgent)}[kind]
+    import tempfile
+
+    d = tempfile.mkdtemp()
+    env = Env(num_nodes=20, batch_size=256, seed=123)
+    agent = Agent(seed=123, csv_path=os.path.join(d, "log.csv"))
+    epochs = 80
+    agent.train(env, epochs=epochs, check_point_dir=d + "/ck/")
+    log = np.loadtxt(os.path.join(d, "log.csv"), delimiter=",", skiprows=1)
+    assert log.shape == (epochs, 5) and np.array_equal(log[:, 0], np.arange(epochs))
+    assert os.path.exists(os.path.join(d, "ck", "model_epoch_50.pt"))          # saved every 50th epoch, like the reference
+    cost, ref_cost = -log[:, 2], -ref[:epochs, 2]
+    assert abs(cost[0] - ref_cost[0]) < 0.35                                     # epoch 0: same instances, untrained sampling
+    for lo in (10, 30, 60):                                                      # 10-epoch windows
+        a, b = cost[lo:lo + 10].mean(), ref_cost[lo:lo + 10].mean()
+        assert abs(a - b) <= 0.06 * b, (kind, lo, a, b)
+    assert cost[-10:].mean() < 0.62 * cost[0]
