@@ -224,27 +224,49 @@ __global__ void __launch_bounds__(256) k_enc_attention_f16(const float* __restri
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
   const float* base = qkv + b * N * 384;
+  // Staging: ALL global loads of the thread are issued before the first value is converted (the source-level profile of
+  // the one-load-one-convert loops showed 38 % of the kernel's stall samples on the first use of a just-loaded value).
   // K: thread -> (key n, head hh, lane slot t): dims 2t, 2t+1 and 2t+8, 2t+9 of the head
-  for (int i = tid; i < NP * 32; i += 256) {
+  constexpr int KIT = NP * 32 / 256;   // 2 NJJ iterations
+  float2 klo[KIT], khi[KIT];
+#pragma unroll
+  for (int it = 0; it < KIT; ++it) {
+    const int i = tid + it * 256;
     const int t = i & 3, hh = (i >> 3) & 7, n = ((i >> 6) << 1) | ((i >> 2) & 1);   // a quarter warp stores keys n, n+1
-    float2 lo2 = make_float2(0.f, 0.f), hi2 = lo2;
+    klo[it] = khi[it] = make_float2(0.f, 0.f);
     if (n < N) {
       const float* kp = base + (int64_t)n * 384 + 128 + hh * 16 + 2 * t;
-      lo2 = *reinterpret_cast<const float2*>(kp);
-      hi2 = *reinterpret_cast<const float2*>(kp + 8);
+      klo[it] = __ldg(reinterpret_cast<const float2*>(kp));
+      khi[it] = __ldg(reinterpret_cast<const float2*>(kp + 8));
     }
-    const uint2 p0 = split_f16x2_u(lo2.x, lo2.y), p1 = split_f16x2_u(hi2.x, hi2.y);
-    Kf[(hh * NP + n) * 4 + t] = make_uint4(p0.x, p1.x, p0.y, p1.y);
   }
   // V: thread -> (k16 step jj, lane slot t, 4 consecutive dims c4..c4+3 of the 128): keys 16jj+2t, +1 and 16jj+2t+8, +9
-  for (int i = tid; i < NJJ * 4 * 32; i += 256) {
+  constexpr int VIT = (NJJ * 4 * 32 + 255) / 256;
+  float4 vv[VIT][4];
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    const int i = tid + it * 256;
     const int t = i & 3, c4 = ((i >> 2) & 31) * 4, jj = i >> 7;
-    float4 v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int n = 16 * jj + 2 * t + (k & 1) + 8 * (k >> 1);
-      v[k] = (n < N) ? *reinterpret_cast<const float4*>(base + (int64_t)n * 384 + 256 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vv[it][k] = (i < NJJ * 4 * 32 && n < N) ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)n * 384 + 256 + c4))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+#pragma unroll
+  for (int it = 0; it < KIT; ++it) {
+    const int i = tid + it * 256;
+    const int t = i & 3, hh = (i >> 3) & 7, n = ((i >> 6) << 1) | ((i >> 2) & 1);
+    const uint2 p0 = split_f16x2_u(klo[it].x, klo[it].y), p1 = split_f16x2_u(khi[it].x, khi[it].y);
+    Kf[(hh * NP + n) * 4 + t] = make_uint4(p0.x, p1.x, p0.y, p1.y);
+  }
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    const int i = tid + it * 256;
+    if (i >= NJJ * 4 * 32) break;
+    const int t = i & 3, c4 = ((i >> 2) & 31) * 4, jj = i >> 7;
+    const float4* v = vv[it];
     const float e[4][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w},
                            {v[2].x, v[2].y, v[2].z, v[2].w}, {v[3].x, v[3].y, v[3].z, v[3].w}};
     const int hh = c4 >> 4, d0 = c4 & 15;
