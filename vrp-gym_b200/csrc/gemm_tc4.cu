@@ -31,13 +31,15 @@ namespace vrpx {
 namespace tc4 {
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;                      // general shapes: 3 stages of X + W boxes
+constexpr int STAGES_K128 = 4;                 // K = 128: W resident, 4 stages of X boxes (see K128 below)
 constexpr int NTHREADS = 512;
 constexpr int TILE_BYTES = 16 * 1024;          // every TMA box: 128 rows x 128 bytes
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // X raw k 0..31 | X raw k 32..63 | W hi | W lo   (X hi/lo live in TMEM)
 constexpr uint32_t TMEM_A0 = 2 * BN;            // TMEM columns: 2 accumulators, then STAGES x (32 hi + 32 lo) A columns
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 + 1024;   // stages | 8 epilogue transpose patches | alignment slack
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;   // = STAGES_K128 x (2 X boxes) + 4 resident W boxes
+constexpr int SMEM_BYTES = RING_BYTES + 8 * 4096 + 1024;   // ring | 8 epilogue transpose patches | alignment slack
 // kind::f16: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -74,12 +76,20 @@ __global__ void k_split_w16(const float* __restrict__ W, __half* __restrict__ hi
 // error, which the decoder's 10·tanh pointer logits amplify to the 1e-5 parity bound); with the cross terms apart the
 // full-magnitude chain is 64 long and the other 128 additions happen at 2^-11 of the magnitude.  Costs the accumulator
 // double buffering (the epilogue of a tile no longer overlaps the MMAs of the next): used for K >= 1024 only.
-template <bool RES, bool GATE, bool SPLITACC>
+//
+// K128 (K = 128: QKV, out-proj, the decoder's query folds): a CTA keeps ONE column tile for its whole life, so its 64 KiB of
+// split weights (hi / lo x two k blocks) are loaded ONCE and stay resident; the ring then carries only the raw X boxes —
+// four stages of 32 KiB = two row tiles of lookahead.  With W in the ring and both k blocks held until the tile's last
+// MMA (cross-terms-first order) the producer could run only one stage ahead: the QKV GEMM took 1.64 ms for 6.7 GB.
+template <bool RES, bool GATE, bool SPLITACC, bool K128>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh,
            const __grid_constant__ CUtensorMap mapWl) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t s_raw_full[STAGES], s_conv_done[STAGES], s_stage_free[STAGES], s_acc_full[2], s_acc_free[2];
+  constexpr int NST = K128 ? STAGES_K128 : STAGES;                    // ring depth
+  constexpr int XST = K128 ? 2 * TILE_BYTES : STAGE_BYTES;            // bytes per ring stage
+  __shared__ __align__(8) uint64_t s_raw_full[STAGES_K128], s_conv_done[STAGES_K128], s_stage_free[STAGES_K128], s_acc_full[2],
+      s_acc_free[2], s_w_full;
   __shared__ uint32_t s_tmem;
   // 1 KiB alignment (SWIZZLE_128B atoms) by an OFFSET into the extern array: pointer arithmetic keeps the shared address
   // space, so the converters and the epilogue get LDS / STS instead of generic loads and stores
@@ -96,7 +106,8 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
   const int nkb = a.K / BK;
 
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    mbar_init(smem_u32(&s_w_full), 1);
+    for (int i = 0; i < NST; ++i) {
       mbar_init(smem_u32(&s_raw_full[i]), 1);
       mbar_init(smem_u32(&s_conv_done[i]), 4);
       mbar_init(smem_u32(&s_stage_free[i]), 1);
@@ -120,18 +131,29 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t kbc = 0;
+      if (K128) {   // the resident weights: [k block][hi | lo] behind the X ring
+        unsigned char* wr = smem + NST * XST;
+        const uint32_t bar = smem_u32(&s_w_full);
+        mbar_expect_tx(bar, 4 * TILE_BYTES);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(smem_u32(wr + (2 * kb) * TILE_BYTES), &mapWh, kb * BK, col0, bar);
+          tma_load_2d(smem_u32(wr + (2 * kb + 1) * TILE_BYTES), &mapWl, kb * BK, col0, bar);
+        }
+      }
       for (int64_t rt = rt0; rt < nrt; rt += rts) {
         const int row0 = (int)rt * BM;
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-          const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
+          const uint32_t s = kbc % NST, ph = (kbc / NST) & 1;
           mbar_wait(smem_u32(&s_stage_free[s]), ph ^ 1);
-          unsigned char* st = smem + s * STAGE_BYTES;
+          unsigned char* st = smem + s * XST;
           const uint32_t bar = smem_u32(&s_raw_full[s]);
-          mbar_expect_tx(bar, STAGE_BYTES);
+          mbar_expect_tx(bar, XST);
           tma_load_2d(smem_u32(st), &mapX, kb * BK, row0, bar);
           tma_load_2d(smem_u32(st + TILE_BYTES), &mapX, kb * BK + 32, row0, bar);
-          tma_load_2d(smem_u32(st + 2 * TILE_BYTES), &mapWh, kb * BK, col0, bar);
-          tma_load_2d(smem_u32(st + 3 * TILE_BYTES), &mapWl, kb * BK, col0, bar);
+          if (!K128) {
+            tma_load_2d(smem_u32(st + 2 * TILE_BYTES), &mapWh, kb * BK, col0, bar);
+            tma_load_2d(smem_u32(st + 3 * TILE_BYTES), &mapWl, kb * BK, col0, bar);
+          }
         }
       }
     }
@@ -140,8 +162,8 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     uint32_t kbc = 0;
     for (int64_t rt = rt0; rt < nrt; rt += rts) {
       for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-        const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
-        unsigned char* st = smem + s * STAGE_BYTES;
+        const uint32_t s = kbc % NST, ph = (kbc / NST) & 1;
+        unsigned char* st = smem + s * XST;
         mbar_wait(smem_u32(&s_raw_full[s]), ph);
         x_tile_to_tmem(st, tid, tmem + ((uint32_t)(warp * 32) << 16) + TMEM_A0 + s * 64);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -158,12 +180,13 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
         mbar_wait(smem_u32(&s_acc_free[acc]), aph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem + acc * BN, dx = SPLITACC ? tmem + BN : d;   // main / cross-term accumulators
-        if (!SPLITACC && nkb == 2) {
+        if (K128) {
           // K = 128 (QKV, out-proj, FF1, the K = 128 backward products): both k blocks are resident (3 stages), so ALL
           // cross terms are issued before the first main term.  The truncating accumulations of the 16 cross-term MMAs
           // then happen while the accumulator holds only the 2^-11-sized cross sum; the full-magnitude chain is the 8
           // main MMAs (measured bias of the result: -1.5e-7 instead of -3.8e-7 relative, like SPLITACC, at no TMEM cost).
-          const uint32_t s0 = kbc % STAGES, ph0 = (kbc / STAGES) & 1, s1 = (kbc + 1) % STAGES, ph1 = ((kbc + 1) / STAGES) & 1;
+          const uint32_t s0 = kbc % NST, ph0 = (kbc / NST) & 1, s1 = (kbc + 1) % NST, ph1 = ((kbc + 1) / NST) & 1;
+          if (ti == 0) mbar_wait(smem_u32(&s_w_full), 0);
           mbar_wait(smem_u32(&s_conv_done[s0]), ph0);
           mbar_wait(smem_u32(&s_conv_done[s1]), ph1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -172,9 +195,9 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
           for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
-              unsigned char* st = smem + sidx[kb] * STAGE_BYTES;
+              unsigned char* wr = smem + NST * XST + (2 * kb) * TILE_BYTES;   // resident W of this k block: hi | lo
               const uint32_t ah = tmem + TMEM_A0 + sidx[kb] * 64, alo = ah + 32;
-              const uint64_t wh = make_desc(smem_u32(st + 2 * TILE_BYTES)), wl = make_desc(smem_u32(st + 3 * TILE_BYTES));
+              const uint64_t wh = make_desc(smem_u32(wr)), wl = make_desc(smem_u32(wr + TILE_BYTES));
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j) {
                 const uint64_t o = (uint64_t)(2 * j);
@@ -193,8 +216,8 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
           continue;
         }
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-          const uint32_t s = kbc % STAGES, ph = (kbc / STAGES) & 1;
-          unsigned char* st = smem + s * STAGE_BYTES;
+          const uint32_t s = kbc % NST, ph = (kbc / NST) & 1;
+          unsigned char* st = smem + s * XST;
           mbar_wait(smem_u32(&s_conv_done[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t ah = tmem + TMEM_A0 + s * 64, alo = ah + 32;
@@ -219,7 +242,7 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
     // instruction of the warp covers 4 rows x 128 contiguous bytes.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int chalf = (warp - 8) >> 2;   // this warp's pair of 32-column chunks
-    unsigned char* patch = smem + STAGES * STAGE_BYTES + (warp - 8) * 4096;
+    unsigned char* patch = smem + RING_BYTES + (warp - 8) * 4096;
     const int lr = lane >> 3, lc = lane & 7;
     const float relu_floor = a.relu ? 0.f : -INFINITY;
     // per-column epilogue constants of this warp's two 32-column chunks (4 columns per lane after the transpose)
@@ -322,6 +345,22 @@ k_gemm_tc4(GemmArgs a, const __grid_constant__ CUtensorMap mapX, const __grid_co
   }
 }
 
+typedef void (*GemmKernel)(GemmArgs, const CUtensorMap, const CUtensorMap, const CUtensorMap);
+static GemmKernel kernel_variant(int v) {
+  switch (v) {
+    case 9: return k_gemm_tc4<true, true, false, true>;
+    case 8: return k_gemm_tc4<false, true, false, true>;
+    case 7: return k_gemm_tc4<true, false, false, true>;
+    case 6: return k_gemm_tc4<false, false, false, true>;
+    case 5: return k_gemm_tc4<true, false, true, false>;
+    case 4: return k_gemm_tc4<false, false, true, false>;
+    case 3: return k_gemm_tc4<true, true, false, false>;
+    case 2: return k_gemm_tc4<false, true, false, false>;
+    case 1: return k_gemm_tc4<true, false, false, false>;
+    default: return k_gemm_tc4<false, false, false, false>;
+  }
+}
+
 int split_weights(const float* W, __half* w16, int n, cudaStream_t stream) {
   k_split_w16<<<(n + 255) / 256, 256, 0, stream>>>(W, w16, w16 + n, n);
   VRPX_LAUNCH_CHECK();
@@ -359,12 +398,7 @@ int gemm_tc_plan(const GemmArgs& a, __half* w16, GemmPlan* pl, cudaStream_t stre
     VRPX_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(attr_mu);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tc4<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      for (int v = 0; v < 10; ++v) VRPX_CUDA(cudaFuncSetAttribute(kernel_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -377,21 +411,14 @@ int gemm_tc_plan(const GemmArgs& a, __half* w16, GemmPlan* pl, cudaStream_t stre
   pl->a = a;
   pl->grid = (int)(per_ct * nct);
   const bool split_acc = (g_force_split_acc ? g_force_split_acc > 0 : a.K >= 1024) && !a.gate;   // see SPLITACC
-  pl->variant = split_acc ? (a.residual ? 5 : 4) : ((a.residual ? 1 : 0) | (a.gate ? 2 : 0));
+  // variants: 0-3 general (bit 0 residual, bit 1 gate), 4-5 split accumulators (+ residual), 6-9 K = 128 (bit 0 residual, bit 1 gate)
+  pl->variant = split_acc ? (a.residual ? 5 : 4) : ((a.K == 2 * BK ? 6 : 0) + ((a.residual ? 1 : 0) | (a.gate ? 2 : 0)));
   return VRPX_OK;
 }
 
 int gemm_tc_launch(const GemmPlan& pl, cudaStream_t stream) {
   using namespace tc4;
-  const GemmArgs& a = pl.a;
-  switch (pl.variant) {
-    case 5: k_gemm_tc4<true, false, true><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
-    case 4: k_gemm_tc4<false, false, true><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
-    case 3: k_gemm_tc4<true, true, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
-    case 2: k_gemm_tc4<false, true, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
-    case 1: k_gemm_tc4<true, false, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
-    default: k_gemm_tc4<false, false, false><<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(a, pl.mx, pl.mwh, pl.mwl); break;
-  }
+  kernel_variant(pl.variant)<<<pl.grid, NTHREADS, SMEM_BYTES, stream>>>(pl.a, pl.mx, pl.mwh, pl.mwl);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }

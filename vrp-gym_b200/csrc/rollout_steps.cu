@@ -38,6 +38,24 @@ __device__ __forceinline__ bool episode_over(const RolloutParams& p, int trel) {
   return trel > 0 && ld_acquire_i(p.notdone + trel - 1) == 0;
 }
 
+// A finished VRP / IRP instance idles on its depot until the slowest instance of the batch is done (tsp.py:103-104): all
+// nodes are visited and the vehicle stands on the depot, so rule R3 leaves the depot as the ONLY feasible node.  Its action
+// (the depot), its reward (0), its log-prob (log 1 = 0 exactly) do not depend on the logits, so the step kernels skip
+// the glimpse and the embedding gather for it — unless the caller asked for the logits themselves (tests).  `own` = the
+// instance's decoder-visible mask words.  (At the depot rule R1 masks the depot unless everything is visited, so
+// "the depot is the only candidate while cur == depot" is exactly "finished".)
+__device__ __forceinline__ bool instance_idle(const uint32_t (&own)[4], int N, int cur, int depot) {
+  if (cur != depot) return false;
+  int cand = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rem = N - 32 * i;
+    const uint32_t range = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+    cand += __popc(~own[i] & range);
+  }
+  return cand == 1 && !((own[depot >> 5] >> (depot & 31)) & 1u);
+}
+
 // ---------------------------------------------------------------- glimpse: tables -> softmax -> c
 __global__ void __launch_bounds__(GW_MAX * 32, 2) k_step_glimpse(const RolloutParams p, int t) {
   extern __shared__ __align__(16) unsigned char gsm[];
@@ -60,6 +78,16 @@ __global__ void __launch_bounds__(GW_MAX * 32, 2) k_step_glimpse(const RolloutPa
     cp_async_commit();
   };
   const int nsl = (N + 7) / 8;
+  if (kind != VRPX_TSP && !p.logits) {   // idle finished instance: its step needs no glimpse and no embeddings (see instance_idle)
+    uint32_t own[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) own[i] = __ldcg(p.env.mask + b * 4 + i);
+    if (instance_idle(own, N, __ldcg(p.env.cur + b), __ldg(p.env.depot + b))) {
+      if (p.mask_hist && lane < 4) p.mask_hist[((int64_t)trel * B + b) * 4 + lane] = __ldcg(p.env.mask + b * 4 + lane);
+      if (p.load_hist && lane == 0) p.load_hist[(int64_t)trel * B + b] = (float)p.env.load[b];
+      return;
+    }
+  }
 #pragma unroll
   for (int sidx = 0; sidx < GNS; ++sidx) {
     if (sidx < nsl) issue_slice(sidx);
@@ -237,7 +265,9 @@ __global__ void __launch_bounds__(SW * 32) k_step_pointer(const RolloutParams p,
       cand[i] = ~mw[i] & range;
       cum[i + 1] = cum[i] + __popc(cand[i]);
     }
-    const int total = cum[4];
+    // idle finished instance (see instance_idle): the depot is the only candidate and nobody reads its logit
+    const bool idle = kind != VRPX_TSP && !p.logits && instance_idle(mw, N, __ldcg(p.env.cur + b), __ldg(p.env.depot + b));
+    const int total = idle ? 0 : cum[4];
     // lanes 0..7 resolve the node index of candidate j0 + lane (-1 beyond the list)
     auto resolve = [&](int j0) {
       int idx = -1;
@@ -282,7 +312,7 @@ __global__ void __launch_bounds__(SW * 32) k_step_pointer(const RolloutParams p,
     for (int i = 0; i < 4; ++i) {
       const int n = lane * 4 + i;
       const bool ok = n < N && !((mw[n >> 5] >> (n & 31)) & 1u);
-      u[i] = ok ? slot[n] : -INFINITY;
+      u[i] = ok ? (idle ? 0.f : slot[n]) : -INFINITY;   // idle: one candidate, any finite logit gives action = depot, log-prob 0
     }
     if (p.logits) {
       float* lo = p.logits + ((int64_t)trel * B + b) * N;
