@@ -268,25 +268,34 @@ __global__ void __launch_bounds__(SW * 32) k_step_pointer(const RolloutParams p,
     // idle finished instance (see instance_idle): the depot is the only candidate and nobody reads its logit
     const bool idle = kind != VRPX_TSP && !p.logits && instance_idle(mw, N, __ldcg(p.env.cur + b), __ldg(p.env.depot + b));
     const int total = idle ? 0 : cum[4];
-    // lanes 0..7 resolve the node index of candidate j0 + lane (-1 beyond the list)
-    auto resolve = [&](int j0) {
-      int idx = -1;
-      const int j = j0 + lane;
-      if (lane < 8 && j < total) {
+    // The candidate list is resolved ONCE: lane l holds the node indices of candidates l, l + 32, l + 64, l + 96 (-1 beyond
+    // the list), so the gather loop below takes its row indices from registers (find-nth-set-bit inside the loop sat on
+    // the critical path of every 8-row chunk).
+    int cidx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = lane + 32 * k;
+      cidx[k] = -1;
+      if (j < total) {
         const int w = (j >= cum[1]) + (j >= cum[2]) + (j >= cum[3]);
         const uint32_t word = w == 0 ? cand[0] : (w == 1 ? cand[1] : (w == 2 ? cand[2] : cand[3]));
         const int base_cnt = w == 0 ? 0 : (w == 1 ? cum[1] : (w == 2 ? cum[2] : cum[3]));
-        idx = 32 * w + (int)__fns(word, 0, j - base_cnt + 1);
+        cidx[k] = 32 * w + (int)__fns(word, 0, j - base_cnt + 1);
       }
-      return idx;
+    }
+    // node index of candidate j (warp-uniform j): from the lane / register that resolved it
+    auto cand_node = [&](int j) {
+      const int k = j >> 5;
+      const int v = k == 0 ? cidx[0] : (k == 1 ? cidx[1] : (k == 2 ? cidx[2] : cidx[3]));
+      return (j < total) ? __shfl_sync(0xffffffffu, v, j & 31) : -1;
     };
     {
-      int myidx = resolve(0);
       float4 nxt[8];
+      int nn[8];   // nodes of the chunk in flight
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int n = __shfl_sync(0xffffffffu, myidx, i);
-        nxt[i] = (n >= 0) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nn[i] = cand_node(i);
+        nxt[i] = (nn[i] >= 0) ? __ldg(hp + nn[i] * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int j0 = 0; j0 < total; j0 += 8) {
         float v[8];
@@ -295,12 +304,14 @@ __global__ void __launch_bounds__(SW * 32) k_step_pointer(const RolloutParams p,
           const float4 hv = nxt[i];
           v[i] = fmaf(qh.x, hv.x, fmaf(qh.y, hv.y, fmaf(qh.z, hv.z, qh.w * hv.w)));
         }
-        const int nsel = __shfl_sync(0xffffffffu, myidx, (lane >> 2) & 7);   // node of the sum this lane group reduces
-        myidx = resolve(j0 + 8);
+        int nsel = -1;   // node of the sum this lane group reduces: candidate j0 + ((lane >> 2) & 7)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (((lane >> 2) & 7) == i) nsel = nn[i];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int n = __shfl_sync(0xffffffffu, myidx, i);
-          nxt[i] = (n >= 0) ? __ldg(hp + n * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          nn[i] = cand_node(j0 + 8 + i);
+          nxt[i] = (nn[i] >= 0) ? __ldg(hp + nn[i] * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float sc = reduce8(v, lane);
         if ((lane & 3) == 0 && nsel >= 0) slot[nsel] = 10.0f * tanhf(sc);
