@@ -522,7 +522,7 @@ __device__ __forceinline__ void warp_glimpse_scores(const float* q, const float4
 }
 
 constexpr int FW = 8;   // warps (= instances) per CTA of the first-step glimpse kernel
-__global__ void __launch_bounds__(FW * 32) k_step_glimpse_first(const RolloutParams p, int t) {
+__global__ void __launch_bounds__(FW * 32, 2) k_step_glimpse_first(const RolloutParams p, int t) {
   __shared__ __align__(16) float s_slot[FW][QW];
   const int trel = t - p.t0;
   if (episode_over(p, trel)) return;
