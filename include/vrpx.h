@@ -320,6 +320,15 @@ VRPX_API int vrpx_debug_ff_fused(const float* X, int64_t R, const float* W1, con
                                  void* stream);
 VRPX_API void vrpx_debug_encoder_fuse_ff(int32_t enable);
 
+/* Test / measurement hooks of the fused QKV-projection + self-attention kernel (csrc/attn_fused.cu):
+ *   vrpx_debug_qkv_attention            att [B·N][128] = MultiheadAttention core (8 heads, no out-projection) of
+ *                                       X [B·N][128] with in_proj_w [384][128], in_proj_b [384] (graph_encoder.py:74-104)
+ *   vrpx_debug_encoder_fuse_attention   1 (default): vrpx_encoder_forward runs projection + attention through that kernel
+ *                                       whenever no activations are saved; 0: GEMM + attention kernel (A/B measurements) */
+VRPX_API int vrpx_debug_qkv_attention(const float* X, const float* in_proj_w, const float* in_proj_b, int64_t B, int32_t N,
+                                      float* att, void* stream);
+VRPX_API void vrpx_debug_encoder_fuse_attention(int32_t enable);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 VRPX_API int64_t vrpx_launch_count(void);
 

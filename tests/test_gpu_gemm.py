@@ -127,3 +127,31 @@ def test_ff_fused_kernel(R, affine):
                                               vrpx.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert torch.equal(Y, Y2)
+
+
+@pytest.mark.parametrize("B,N", [(1, 50), (7, 50), (300, 50), (5, 20), (33, 21), (9, 10), (4, 100), (3, 101), (2, 128), (3, 2),
+                                 (148 * 2 * 3 + 5, 50), (11, 64), (6, 65), (5, 7)])
+def test_qkv_attention_fused_kernel(B, N):
+    """csrc/attn_fused.cu: the in-projection and the 8-head self-attention of an encoder layer in one kernel (Q, K, V stay
+    in shared memory) against float64 (graph_encoder.py:74-104 = nn.MultiheadAttention without its out-projection);
+    whole-instance tiles for every N bucket, ragged last tiles, odd N."""
+    import vrpx
+
+    dev = vrpx.require_device()
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + N)
+    X = torch.randn(B * N, 128, generator=g).to(dev)
+    W = (torch.randn(384, 128, generator=g) / 128 ** 0.5).to(dev)
+    b = (torch.randn(384, generator=g) * 0.1).to(dev)
+    qkv = (X.double() @ W.double().T + b.double()).view(B, N, 3, 8, 16)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))     # [B][8][N][16]
+    p = torch.softmax(q @ k.transpose(-1, -2) / 4.0, dim=-1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(B * N, 128)
+    att = torch.full((B * N, 128), float("nan"), device=dev)
+    vrpx.check(vrpx.lib().vrpx_debug_qkv_attention(vrpx.ptr(X), vrpx.ptr(W), vrpx.ptr(b), B, N, vrpx.ptr(att), vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    err = (att.double() - ref).abs().max().item()
+    assert err <= 1e-5 * max(ref.abs().max().item(), 1.0), (B, N, err)
+    att2 = torch.empty_like(att)
+    vrpx.check(vrpx.lib().vrpx_debug_qkv_attention(vrpx.ptr(X), vrpx.ptr(W), vrpx.ptr(b), B, N, vrpx.ptr(att2), vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(att, att2)

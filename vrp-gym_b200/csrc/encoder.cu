@@ -467,7 +467,8 @@ constexpr int64_t kSavedStatFloats = 2 * VRPX_LAYERS * 2 * 128;                 
 
 using namespace vrpx;
 
-static int g_fuse_ff = 1;   // vrpx_debug_encoder_fuse_ff
+static int g_fuse_ff = 1;     // vrpx_debug_encoder_fuse_ff
+static int g_fuse_attn = 1;   // vrpx_debug_encoder_fuse_attention
 namespace vrpx { extern int g_ff_dbg; }
 
 extern "C" {
@@ -475,6 +476,15 @@ extern "C" {
 void vrpx_debug_encoder_fuse_ff(int32_t enable) {
   g_fuse_ff = enable & 1;
   vrpx::g_ff_dbg = enable >> 1;   // bits above 0: measurement switches of the kernel (ff_fused.cu, Args::dbg)
+}
+
+void vrpx_debug_encoder_fuse_attention(int32_t enable) { g_fuse_attn = enable & 1; }
+
+int vrpx_debug_qkv_attention(const float* X, const float* in_proj_w, const float* in_proj_b, int64_t B, int32_t N, float* att,
+                             void* stream) {
+  VRPX_CHECK_ARG(X && in_proj_w && att, "NULL argument");
+  VRPX_DEVICE_GUARD(X);
+  return qkv_attention_fused(X, in_proj_w, in_proj_b, B, N, att, (cudaStream_t)stream);
 }
 
 int vrpx_debug_ff_fused(const float* X, int64_t R, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -556,13 +566,17 @@ int vrpx_encoder_forward(const vrpx_encoder_weights* w, const vrpx_env* env, con
         hout = (l + 1 < VRPX_LAYERS) ? saved + (int64_t)(l + 1) * R * 128 : h + b0 * N * E;
       }
       int rc = 0;
-      GemmArgs g1{hc, R, E, L.in_proj_w, 3 * E, L.in_proj_b, 0, nullptr, nullptr, nullptr, qkv};
-      if ((rc = gemm(g1, stream))) return rc;
-      if (gemm_path == 1) {  // fp32 SIMT cross-check path
-        k_enc_attention<<<(unsigned)Bc, 256, attn_smem, stream>>>(qkv, att, N);
-        VRPX_LAUNCH_CHECK();
-      } else if ((rc = launch_attention(qkv, att, Bc, N, stream))) {
-        return rc;
+      if (gemm_path == 0 && !saved && g_fuse_attn) {   // Q, K, V stay on chip (attn_fused.cu)
+        if ((rc = qkv_attention_fused(hc, L.in_proj_w, L.in_proj_b, Bc, N, att, stream))) return rc;
+      } else {
+        GemmArgs g1{hc, R, E, L.in_proj_w, 3 * E, L.in_proj_b, 0, nullptr, nullptr, nullptr, qkv};
+        if ((rc = gemm(g1, stream))) return rc;
+        if (gemm_path == 1) {  // fp32 SIMT cross-check path
+          k_enc_attention<<<(unsigned)Bc, 256, attn_smem, stream>>>(qkv, att, N);
+          VRPX_LAUNCH_CHECK();
+        } else if ((rc = launch_attention(qkv, att, Bc, N, stream))) {
+          return rc;
+        }
       }
       if (!train) {
         GemmArgs g2{att, R, E, L.out_proj_w, E, L.out_proj_b, 0, hc, s1->scale, s1->shift, hc};

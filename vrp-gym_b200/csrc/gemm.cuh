@@ -42,6 +42,10 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream);       // production: tcgen0
 int ff_fused(const float* X, int64_t R, const float* W1, const float* b1, const float* W2, const float* b2,
              const float* residual, const float* scale, const float* shift, float* Y, cudaStream_t stream);
 
+// QKV projection + per-instance self-attention of an encoder layer in one kernel (attn_fused.cu)
+int qkv_attention_fused(const float* X, const float* in_proj_w, const float* in_proj_b, int64_t B, int N, float* att,
+                        cudaStream_t stream);
+
 // path: 0 tcgen05 f16-split (production), 1 fp32 SIMT (cross-check: separates tensor-core error from algorithmic error)
 inline int gemm_dispatch(int path, const GemmArgs& a, cudaStream_t stream) {
   if (path != 0 && path != 1) {
