@@ -13,13 +13,34 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reproduction_script_csv(tmp_path):
+    """reproduction.py with a trained checkpoint (tests/golden/ckpt_vrp_20_123.pt, made by make_checkpoints.py with the
+    reference's own training loop): CSV schema of the reference, trained agent clearly better than the random agent."""
     out = tmp_path / "res.csv"
-    subprocess.check_call([sys.executable, os.path.join(ROOT, "vrp-gym_b200", "reproduction.py"), "--env_type", "VRP", "--num_nodes", "10",
-                           "--batch_size", "32", "--seeds", "1234", "--csv_path", str(out), "--model_path", "none"], cwd=tmp_path)
+    script = os.path.join(ROOT, "vrp-gym_b200", "reproduction.py")
+    ckpt = os.path.join(ROOT, "tests", "golden", "ckpt_vrp_20_123.pt")
+    subprocess.check_call([sys.executable, script, "--env_type", "VRP", "--num_nodes", "20", "--batch_size", "32", "--seeds", "1234",
+                           "--csv_path", str(out), "--model_path", ckpt], cwd=tmp_path)
     rows = list(csv.reader(open(out)))
     assert rows[0] == ["Model", "Seed", "Mean Distance"] and len(rows) == 1 + 2 * 32
     assert rows[1][0] == "VRP-Agent" and rows[2][0] == "VRP-Random-Agent"
     assert all(float(r[2]) < 0 for r in rows[1:])  # rewards are negative tour lengths (tsp.py:98)
+    agent = [float(r[2]) for r in rows[1:] if r[0] == "VRP-Agent"]
+    rand = [float(r[2]) for r in rows[1:] if r[0] == "VRP-Random-Agent"]
+    assert sum(agent) / len(agent) > sum(rand) / len(rand) + 1.0
+
+
+def test_reproduction_script_missing_checkpoint(tmp_path):
+    """A missing checkpoint is an error like in the reference (reproduction.py:44), not a silent fallback; with
+    --allow_untrained the rows are labelled as untrained."""
+    out = tmp_path / "res.csv"
+    script = os.path.join(ROOT, "vrp-gym_b200", "reproduction.py")
+    args = [sys.executable, script, "--env_type", "VRP", "--num_nodes", "10", "--batch_size", "8", "--seeds", "1234",
+            "--csv_path", str(out), "--model_path", "none"]
+    res = subprocess.run(args, cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode != 0 and "FileNotFoundError" in res.stderr
+    subprocess.check_call(args + ["--allow_untrained"], cwd=tmp_path)
+    rows = list(csv.reader(open(out)))
+    assert len(rows) == 1 + 2 * 8 and rows[1][0] == "VRP-Agent-untrained"
 
 
 def test_training_checkpoint_roundtrip(tmp_path):

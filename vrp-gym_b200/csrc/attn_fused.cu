@@ -71,7 +71,9 @@ __global__ void k_prepare_inproj(const float* __restrict__ w, __half* __restrict
   wlo[i] = __float2half_rn(x - __half2float(hgh));
 }
 
-template <int NJJ>
+// NK8 = ceil(N / 8) key tiles of the instance: compile-time, so that the unrolled score / softmax / PV loops carry no
+// run-time guards (the only run-time mask is on the tile that straddles N)
+template <int NK8>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_qkv_attention(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh,
                 const __grid_constant__ CUtensorMap mapWl, const float* __restrict__ bias, float* __restrict__ att, int64_t B,
@@ -80,6 +82,7 @@ k_qkv_attention(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   __shared__ __align__(8) uint64_t s_w_full, s_xr_full, s_xr_free, s_xa_full, s_xa_free, s_d_full[2], s_d_free[2];
   __shared__ uint32_t s_tmem;
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  constexpr int NJJ = (NK8 + 1) / 2;               // k16 steps over the keys
   constexpr int VDS = 4 * (NJJ + (NJJ & 1)) + 4;   // chunks (16 B) per dim row of Vf (k_enc_attention_f16)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -316,8 +319,8 @@ k_qkv_attention(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           for (int j = 0; j < 2 * NJJ; j += 2) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) sc[j][e] = sc[j + 1][e] = 0.f;
-            if (8 * j < N) {
-              const bool two = 8 * (j + 1) < N;
+            if (j < NK8) {
+              const bool two = j + 1 < NK8;   // compile-time after unrolling
               const uint4 k0 = Kh[(8 * j + g) * 4 + t];
               const uint4 k1 = two ? Kh[(8 * j + 8 + g) * 4 + t] : make_uint4(0u, 0u, 0u, 0u);
               mma_f16_16x8x16(sc[j], ql, k0.x, k0.y);
@@ -328,8 +331,8 @@ k_qkv_attention(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
               if (two) mma_f16_16x8x16(sc[j + 1], qh, k1.x, k1.y);
 #pragma unroll
               for (int jx = j; jx < j + 2; ++jx) {
-                if (8 * jx >= N) continue;
-                if (8 * jx + 8 > N) {
+                if (jx >= NK8) continue;
+                if (jx == NK8 - 1 && (N & 7)) {
 #pragma unroll
                   for (int e = 0; e < 2; ++e)
                     if (8 * jx + 2 * t + e >= N) { sc[jx][e] = -INFINITY; sc[jx][2 + e] = -INFINITY; }
@@ -344,7 +347,7 @@ k_qkv_attention(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           float sa = 0.f, sb = 0.f;
 #pragma unroll
           for (int j = 0; j < 2 * NJJ; ++j) {
-            if (8 * j < N) {
+            if (j < NK8) {
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 sc[j][e] = ex2_approx(sc[j][e] - ma);          // 2^(-inf) = 0 for the masked keys
@@ -362,7 +365,6 @@ k_qkv_attention(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           for (int d = 0; d < 2; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
 #pragma unroll
           for (int jj = 0; jj < NJJ; ++jj) {
-            if (16 * jj >= N) continue;
             const uint2 p0 = split_f16x2_u(sc[2 * jj][0], sc[2 * jj][1]), p1 = split_f16x2_u(sc[2 * jj][2], sc[2 * jj][3]);
             const uint2 p2 = split_f16x2_u(sc[2 * jj + 1][0], sc[2 * jj + 1][1]), p3 = split_f16x2_u(sc[2 * jj + 1][2], sc[2 * jj + 1][3]);
             const uint32_t ph_[4] = {p0.x, p1.x, p2.x, p3.x}, pl_[4] = {p0.y, p1.y, p2.y, p3.y};
@@ -393,20 +395,21 @@ k_qkv_attention(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   }
 }
 
-template <int NJJ>
+template <int NK8>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const float* bias, float* att, int64_t B,
                   int N, cudaStream_t stream) {
+  constexpr int NJJ = (NK8 + 1) / 2;
   constexpr int VDS = 4 * (NJJ + (NJJ & 1)) + 4;
   int TI = 128 / N;
   if (TI > VF_MAX / (16 * VDS * 16)) TI = VF_MAX / (16 * VDS * 16);
   const int stage_bytes = ST_VF + TI * 16 * VDS * 16;
   const int SMEM_BYTES = SM_STAGE + 2 * stage_bytes + 1024;
-  VRPX_CUDA(cudaFuncSetAttribute(k_qkv_attention<NJJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  VRPX_CUDA(cudaFuncSetAttribute(k_qkv_attention<NK8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t ntiles = (B + TI - 1) / TI;
   int64_t streams = num_sms() / NTYPES;
   if (streams > ntiles) streams = ntiles;
   if (streams < 1) streams = 1;
-  k_qkv_attention<NJJ><<<(unsigned)(streams * NTYPES), NTHREADS, SMEM_BYTES, stream>>>(mx, mwh, mwl, bias, att, B, N, TI, stage_bytes);
+  k_qkv_attention<NK8><<<(unsigned)(streams * NTYPES), NTHREADS, SMEM_BYTES, stream>>>(mx, mwh, mwl, bias, att, B, N, TI, stage_bytes);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }
@@ -432,11 +435,14 @@ int qkv_attention_fused(const float* X, const float* in_proj_w, const float* in_
   if ((rc = make_map(&mx, X, B * N, E, false))) return rc;
   if ((rc = make_map(&mwh, w16, NH * HN, E, true, HN))) return rc;
   if ((rc = make_map(&mwl, w16 + NW, NH * HN, E, true, HN))) return rc;
-  const int njj = (N + 15) / 16;
-  if (njj <= 2) return launch<2>(mx, mwh, mwl, in_proj_b, att, B, N, stream);
-  if (njj <= 4) return launch<4>(mx, mwh, mwl, in_proj_b, att, B, N, stream);
-  if (njj <= 7) return launch<7>(mx, mwh, mwl, in_proj_b, att, B, N, stream);
-  return launch<8>(mx, mwh, mwl, in_proj_b, att, B, N, stream);
+  switch ((N + 7) / 8) {
+#define VRPX_QA_CASE(K) case K: return launch<K>(mx, mwh, mwl, in_proj_b, att, B, N, stream);
+    VRPX_QA_CASE(1) VRPX_QA_CASE(2) VRPX_QA_CASE(3) VRPX_QA_CASE(4) VRPX_QA_CASE(5) VRPX_QA_CASE(6) VRPX_QA_CASE(7) VRPX_QA_CASE(8)
+    VRPX_QA_CASE(9) VRPX_QA_CASE(10) VRPX_QA_CASE(11) VRPX_QA_CASE(12) VRPX_QA_CASE(13) VRPX_QA_CASE(14) VRPX_QA_CASE(15) VRPX_QA_CASE(16)
+#undef VRPX_QA_CASE
+  }
+  set_error("qkv_attention_fused: N=%d out of range", N);
+  return VRPX_ERR_ARG;
 }
 
 }  // namespace vrpx

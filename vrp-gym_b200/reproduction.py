@@ -24,7 +24,13 @@ ENVS = {"TSP": TSPEnv, "VRP": VRPEnv, "IRP": IRPEnv}
 AGENTS = {"TSP": TSPAgent, "VRP": VRPAgent, "IRP": IRPAgent}
 
 
-def reproduce(seeds, num_nodes, batch_size, csv_path, model_path, num_draw, env_type, video=False):
+def reproduce(seeds, num_nodes, batch_size, csv_path, model_path, num_draw, env_type, video=False, allow_untrained=False):
+    # the reference loads the checkpoint unconditionally (reproduction.py:44) and fails without it; so does this script,
+    # unless --allow_untrained asks for seed-initialised weights, which are then labelled as such in the CSV
+    trained = bool(model_path) and os.path.exists(model_path)
+    if not trained and not allow_untrained:
+        raise FileNotFoundError(f"checkpoint {model_path!r} not found (pass --allow_untrained to evaluate seed-initialised weights)")
+    label = f"{env_type}-Agent" if trained else f"{env_type}-Agent-untrained"
     with open(csv_path, "w+", newline="") as f:
         csv.writer(f).writerow(["Model", "Seed", "Mean Distance"])
     for seed in seeds:
@@ -33,10 +39,8 @@ def reproduce(seeds, num_nodes, batch_size, csv_path, model_path, num_draw, env_
         if video:
             env.enable_video_capturing(video_save_path=f"./videos/video_{env_type}_{num_nodes}_{seed}.mp4")
         agent = AGENTS[env_type](seed=seed)
-        if model_path and os.path.exists(model_path):
+        if trained:
             agent.model.load_state_dict(torch.load(model_path, map_location=agent.device))
-        else:
-            print(f"[reproduction] checkpoint {model_path!r} not found: evaluating seed-initialised weights")
         random_agent = RandomAgent(seed=seed)
         random_agent.eval()
         cost_agent = agent.evaluate(env)
@@ -44,7 +48,7 @@ def reproduce(seeds, num_nodes, batch_size, csv_path, model_path, num_draw, env_
         with open(csv_path, "a", newline="") as f:
             w = csv.writer(f)
             for ca, cr in zip(cost_agent.tolist(), cost_random.tolist()):
-                w.writerow([f"{env_type}-Agent", seed, ca])
+                w.writerow([label, seed, ca])
                 w.writerow([f"{env_type}-Random-Agent", seed, cr])
 
 
@@ -58,6 +62,7 @@ if __name__ == "__main__":
     ap.add_argument("--model_path", type=str, default="./check_points/model_epoch__tsp_850.pt")
     ap.add_argument("--env_type", type=str, default="TSP", choices=sorted(ENVS))
     ap.add_argument("--video", action="store_true")
+    ap.add_argument("--allow_untrained", action="store_true", help="evaluate seed-initialised weights when the checkpoint is missing")
     args = ap.parse_args()
     print(vars(args))
     reproduce(**vars(args))
