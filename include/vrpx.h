@@ -299,6 +299,9 @@ VRPX_API int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weigh
  *   C[M][N] += A^T · Bm  with A [R][M], Bm [R][N] (reduction over rows, red.add);  out[c] += sum_r X[r][c];
  *   G[b] = mean_n h[b,n], Xf[b] = h[b, tape0[b]];  dH[b,n] += dG[b]/N, dH[b,tape0[b]] += dXf[b]. */
 VRPX_API int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R, int32_t M, int32_t N, void* stream);
+/* vrpx_gemm_tn_accumulate runs on tcgen05 (csrc/gemm_tn_tc.cu) when M and N are multiples of 128 and R >= 8192;
+ * path 1 forces the warp-level mma.sync kernel for every shape (A/B measurements, cross-check in the tests). */
+VRPX_API void vrpx_debug_gemm_tn_path(int32_t path);
 VRPX_API int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out, void* stream);
 VRPX_API int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B, int32_t N, float* G, float* Xf, void* stream);
 VRPX_API int vrpx_episode_scatter(float* dH, const uint8_t* tape0, int64_t B, int32_t N, const float* dG, const float* dXf,

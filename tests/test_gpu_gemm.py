@@ -155,3 +155,39 @@ def test_qkv_attention_fused_kernel(B, N):
     vrpx.check(vrpx.lib().vrpx_debug_qkv_attention(vrpx.ptr(X), vrpx.ptr(W), vrpx.ptr(b), B, N, vrpx.ptr(att2), vrpx.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert torch.equal(att, att2)
+
+
+@pytest.mark.parametrize("R,M,N,ascale", [(8192, 128, 128, 1.0), (65536 + 37, 128, 512, 1e-5), (100003, 512, 128, 3e-4),
+                                          (50000, 384, 128, 1e-6), (65536, 1024, 128, 1e-4), (9000, 256, 256, 2.0)])
+def test_gemm_tn_tcgen05(R, M, N, ascale):
+    """csrc/gemm_tn_tc.cu: the weight-gradient GEMM on tcgen05 (operands transposed and f16-split on the way into shared
+    memory, split-K with register drains) against float64 — O(1) operands and gradient-sized ones (the A operand is
+    scaled by 2^12 before the split: values down to 1e-6 keep fp32-like relative accuracy), ragged row counts, and
+    against the warp-level kernel it replaces."""
+    import vrpx
+
+    dev = vrpx.require_device()
+    L = vrpx.lib()
+    g = torch.Generator(device="cpu").manual_seed(R + M)
+    A = (torch.randn(R, M, generator=g) * ascale).to(dev)
+    Bm = torch.randn(R, N, generator=g).abs().to(dev)          # activations after a ReLU: the sums do not cancel
+    C = torch.zeros(M, N, device=dev)
+    vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(C), R, M, N, vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    ref = A.double().T @ Bm.double()
+    scale = ref.abs().max().item()
+    err = (C.double() - ref).abs().max().item()
+    assert err <= 2e-5 * scale, (R, M, N, err / scale)
+    L.vrpx_debug_gemm_tn_path(1)
+    try:
+        C1 = torch.zeros(M, N, device=dev)
+        vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(C1), R, M, N, vrpx.stream_ptr(dev)))
+        torch.cuda.synchronize()
+    finally:
+        L.vrpx_debug_gemm_tn_path(0)
+    assert (C1.double() - ref).abs().max().item() <= 2e-5 * scale
+    # accumulation into a non-zero C
+    C2 = C.clone()
+    vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(C2), R, M, N, vrpx.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert (C2.double() - 2 * ref).abs().max().item() <= 4e-5 * scale

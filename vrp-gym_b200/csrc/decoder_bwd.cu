@@ -15,6 +15,7 @@
 //
 // Notation:  q~ = A_l x_l + Q~g (+ load a_load);  s_hn = q~_h·h_n + mask;  p = softmax_n(s);
 // c_h = sum_n p_hn h_n;  q^ = M c + m_c;  z_n = q^·h_n;  u_n = 10 tanh z_n;  pi = softmax(u | unmasked).
+#include "gemm.cuh"
 #include "tile_gemm.cuh"
 
 namespace vrpx {
@@ -782,9 +783,17 @@ int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, co
   return VRPX_OK;
 }
 
+static int g_tn_path = 0;   // vrpx_debug_gemm_tn_path
+void vrpx_debug_gemm_tn_path(int32_t path) { g_tn_path = path; }
+
 int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R, int32_t M, int32_t N, void* stream) {
   VRPX_CHECK_ARG(A && Bm && C && R >= 1 && M >= 1 && N >= 1 && M % 4 == 0 && N % 4 == 0, "bad argument");
   VRPX_DEVICE_GUARD(A);
+  // 128-multiples with enough rows to feed every SM: tcgen05 (gemm_tn_tc.cu); the rest (embedding [128][4], tiny batches)
+  // stays on the warp-level kernels below
+  if (g_tn_path == 0 && M % 128 == 0 && N % 128 == 0 && R >= 8192 && R <= INT32_MAX &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bm) & 15) == 0)
+    return gemm_tn_tc(A, Bm, C, R, M, N, (cudaStream_t)stream);
   int64_t ctas = (R + 2047) / 2048;
   int64_t maxc = (int64_t)num_sms() * 8;
   if (ctas > maxc) ctas = maxc;

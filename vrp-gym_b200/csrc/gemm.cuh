@@ -46,6 +46,9 @@ int ff_fused(const float* X, int64_t R, const float* W1, const float* b1, const 
 int qkv_attention_fused(const float* X, const float* in_proj_w, const float* in_proj_b, int64_t B, int N, float* att,
                         cudaStream_t stream);
 
+// weight-gradient GEMM C [M][N] += A^T · B over the R rows of A [R][M], B [R][N] on tcgen05 (gemm_tn_tc.cu); M, N % 128 == 0
+int gemm_tn_tc(const float* A, const float* Bm, float* C, int64_t R, int M, int N, cudaStream_t stream);
+
 // path: 0 tcgen05 f16-split (production), 1 fp32 SIMT (cross-check: separates tensor-core error from algorithmic error)
 inline int gemm_dispatch(int path, const GemmArgs& a, cudaStream_t stream) {
   if (path != 0 && path != 1) {
