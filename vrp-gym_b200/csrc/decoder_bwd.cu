@@ -16,9 +16,12 @@
 // Notation:  q~ = A_l x_l + Q~g (+ load a_load);  s_hn = q~_h·h_n + mask;  p = softmax_n(s);
 // c_h = sum_n p_hn h_n;  q^ = M c + m_c;  z_n = q^·h_n;  u_n = 10 tanh z_n;  pi = softmax(u | unmasked).
 #include "gemm.cuh"
+#include "glimpse_mma.cuh"
 #include "tile_gemm.cuh"
 
 namespace vrpx {
+
+constexpr int SCQ = 4;   // 1024-float scratch slots per instance
 
 struct DecBwdParams {
   int kind, N, T;
@@ -31,7 +34,7 @@ struct DecBwdParams {
   const float* wts;
   const float *al_t, *a_q0, *a_load, *m_t, *m_c, *m_n, *al_n;
   float *dH, *D0, *D1, *Dl, *d_al_t, *d_m_t, *d_m_c;
-  float* scratch;  // [grid][TM][3][1024]: q~ | p[n][8] | dz[128], q^[128]
+  float* scratch;  // [grid][TM][4][1024]: q~ | p[n][8] | dz[128], q^[128] | dc
 };
 
 // Xs | QC | Wb | DQ with the padded leading dimensions of the tensor-pipe tile GEMMs (XS_LD, QC_LD): 225.5 KiB
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
   const int64_t B = p.B;
   const int64_t ntiles = (B + TM - 1) / TM;
   const float* __restrict__ h = p.h;
-  float* SC = p.scratch + (size_t)blockIdx.x * TM * 3 * QW;
+  float* SC = p.scratch + (size_t)blockIdx.x * TM * SCQ * QW;
   float* su = Wb + warp * 128;  // per-warp scratch for u (Wb is idle outside the GEMM phases)
   float mc_acc = 0.f;           // d m_c[tid] for tid < 128, flushed once at the end
 
@@ -134,39 +137,29 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
       for (int m = warp; m < cnt; m += NT / 32) {
         const int64_t b = base + m;
         float* slot = QC + m * QC_LD;
-        float* sc_q = SC + (size_t)m * 3 * QW;
+        float* sc_q = SC + (size_t)m * SCQ * QW;
         float* sc_p = sc_q + QW;
-        float4 qt[NH];
 #pragma unroll
-        for (int hh = 0; hh < NH; ++hh) {
-          qt[hh] = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
-          *reinterpret_cast<float4*>(sc_q + hh * E + lane * 4) = qt[hh];
-        }
+        for (int hh = 0; hh < NH; ++hh)
+          *reinterpret_cast<float4*>(sc_q + hh * E + lane * 4) = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
         __syncwarp();
-        const int myh = (lane >> 2) & 7;
-        const uint32_t* nbm = p.mask_hist + ((int64_t)t * B + quirk_row(b, myh, p.G)) * 4;
-        uint32_t nb[4];
+        // scores on the tensor pipe (glimpse_mma.cuh); this lane stores heads 2 tq, 2 tq + 1: their partner masks
+        const int tq = lane & 3;
+        uint32_t nb[2][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) nb[i] = nbm[i];
-        const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
-        for (int n0 = 0; n0 < N; n0 += 4) {
-          float4 hv4[4];
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t* nbm = p.mask_hist + ((int64_t)t * B + quirk_row(b, 2 * tq + which, p.G)) * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) hv4[i] = (n0 + i < N) ? __ldg(hp + (n0 + i) * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = n0 + i;
-            if (n < N) {
-              const float4 hv = hv4[i];
-              float v[NH];
-#pragma unroll
-              for (int hh = 0; hh < NH; ++hh)
-                v[hh] = fmaf(qt[hh].x, hv.x, fmaf(qt[hh].y, hv.y, fmaf(qt[hh].z, hv.z, qt[hh].w * hv.w)));
-              float sc = reduce8(v, lane);
-              if ((lane & 3) == 0) slot[myh * E + n] = sc + (float)((nb[n >> 5] >> (n & 31)) & 1u);
-            }
-          }
+          for (int i = 0; i < 4; ++i) nb[which][i] = nbm[i];
         }
+        const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
+        warp_glimpse_scores(slot, hrow, N, lane, [&](int n, int which, float v) {
+          const int wi = n >> 5;
+          const uint32_t w0 = which ? nb[1][0] : nb[0][0], w1 = which ? nb[1][1] : nb[0][1];
+          const uint32_t w2 = which ? nb[1][2] : nb[0][2], w3 = which ? nb[1][3] : nb[0][3];
+          const uint32_t wsel = wi == 0 ? w0 : (wi == 1 ? w1 : (wi == 2 ? w2 : w3));
+          slot[(2 * tq + which) * E + n] = v + (float)((wsel >> (n & 31)) & 1u);
+        });
         __syncwarp();
         float pr[NH][4];
 #pragma unroll
@@ -205,25 +198,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
           }
         }
         __syncwarp();
-        float4 c[NH];
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) c[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int n = 0; n < N; ++n) {
-          const float4 hv = __ldg(hp + n * (E / 4));
-          const float4 p0 = *reinterpret_cast<const float4*>(slot + n * 8);
-          const float4 p1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
-          const float pv[NH] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-          for (int hh = 0; hh < NH; ++hh) {
-            c[hh].x = fmaf(pv[hh], hv.x, c[hh].x);
-            c[hh].y = fmaf(pv[hh], hv.y, c[hh].y);
-            c[hh].z = fmaf(pv[hh], hv.z, c[hh].z);
-            c[hh].w = fmaf(pv[hh], hv.w, c[hh].w);
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) *reinterpret_cast<float4*>(slot + hh * E + lane * 4) = c[hh];
+        warp_glimpse_values(slot, hrow, N, lane);   // c[head][dim] = sum_n p_hn h_n -> slot
       }
       for (int o = cnt * QW + tid; o < TM * QW; o += NT) QC[(o >> 10) * QC_LD + (o & (QW - 1))] = 0.f;
       __syncthreads();
@@ -274,7 +249,7 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
           const float w = s_w[m];
           const int act = s_act[m];
           __syncwarp();
-          float* sc_z = SC + (size_t)m * 3 * QW + 2 * QW;   // dz[0..127] | q^[128..255]
+          float* sc_z = SC + (size_t)m * SCQ * QW + 2 * QW;   // dz[0..127] | q^[128..255]
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             int n = lane * 4 + i;
@@ -366,34 +341,19 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
         for (int hh = 0; hh < NH; ++hh) dq[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < cnt && s_live[m]) {
           const int64_t b = base + m;
-          const float* sc_q = SC + (size_t)m * 3 * QW;
+          const float* sc_q = SC + (size_t)m * SCQ * QW;
           const float* sc_p = sc_q + QW;
           const float* sc_z = sc_q + 2 * QW;
-          const float4* hp = reinterpret_cast<const float4*>(h + b * N * E) + lane;
-          float4 dc[NH];
+          float* sc_dc = SC + (size_t)m * SCQ * QW + 3 * QW;
+          const float4* hrow = reinterpret_cast<const float4*>(h + b * N * E);
+          const int tq = lane & 3;
+          // dc is parked in the scratch (pass Y needs it after the slot has been reused)
 #pragma unroll
-          for (int hh = 0; hh < NH; ++hh) dc[hh] = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
+          for (int hh = 0; hh < NH; ++hh)
+            *reinterpret_cast<float4*>(sc_dc + hh * E + lane * 4) = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
           __syncwarp();
-          const int myh = (lane >> 2) & 7;
-          // dp_hn = dc_h · h_n  -> slot[h][n]
-          for (int n0 = 0; n0 < N; n0 += 4) {
-            float4 hv4[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hv4[i] = (n0 + i < N) ? __ldg(hp + (n0 + i) * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = n0 + i;
-              if (n < N) {
-                const float4 hv = hv4[i];
-                float v[NH];
-#pragma unroll
-                for (int hh = 0; hh < NH; ++hh)
-                  v[hh] = fmaf(dc[hh].x, hv.x, fmaf(dc[hh].y, hv.y, fmaf(dc[hh].z, hv.z, dc[hh].w * hv.w)));
-                float sc = reduce8(v, lane);
-                if ((lane & 3) == 0) slot[myh * E + n] = sc;
-              }
-            }
-          }
+          // dp_hn = dc_h · h_n  -> slot[h][n]   (the score contraction with dc as the query)
+          warp_glimpse_scores(slot, hrow, N, lane, [&](int n, int which, float v) { slot[(2 * tq + which) * E + n] = v; });
           __syncwarp();
           // ds_hn = p_hn (dp_hn - sum_m p_hm dp_hm), lane = node
           float ds[NH][4];
@@ -430,9 +390,12 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
           __syncwarp();
           // pass Y: dH[b,n] += sum_h (p_hn dc_h + ds_hn q~_h) + dz_n q^     (one RMW of dH per node and step)
           {
-            float4 qt[NH];
+            float4 qt[NH], dc[NH];
 #pragma unroll
-            for (int hh = 0; hh < NH; ++hh) qt[hh] = *reinterpret_cast<const float4*>(sc_q + hh * E + lane * 4);
+            for (int hh = 0; hh < NH; ++hh) {
+              qt[hh] = *reinterpret_cast<const float4*>(sc_q + hh * E + lane * 4);
+              dc[hh] = *reinterpret_cast<const float4*>(sc_dc + hh * E + lane * 4);
+            }
             const float4 qh = *reinterpret_cast<const float4*>(sc_z + 128 + lane * 4);
             float4* dhp = reinterpret_cast<float4*>(p.dH + b * N * E) + lane;
             for (int n = 0; n < N; ++n) {
@@ -455,18 +418,11 @@ __global__ void __launch_bounds__(NT, 1) k_decoder_bwd(const DecBwdParams p) {
               dhp[n * (E / 4)] = make_float4(o.x + g.x, o.y + g.y, o.z + g.z, o.w + g.w);
             }
           }
-          // pass X: dq~_h = sum_n ds_hn h_n
-          for (int n = 0; n < N; ++n) {
-            const float4 hv = __ldg(hp + n * (E / 4));
-            const float4 s0 = *reinterpret_cast<const float4*>(slot + n * 8);
-            const float4 s1 = *reinterpret_cast<const float4*>(slot + n * 8 + 4);
-            const float dsv[NH] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          // pass X: dq~_h = sum_n ds_hn h_n   (the value contraction with ds as the probabilities) -> slot[h][dim]
+          __syncwarp();
+          warp_glimpse_values(slot, hrow, N, lane);
 #pragma unroll
-            for (int hh = 0; hh < NH; ++hh) {
-              dq[hh].x = fmaf(dsv[hh], hv.x, dq[hh].x); dq[hh].y = fmaf(dsv[hh], hv.y, dq[hh].y);
-              dq[hh].z = fmaf(dsv[hh], hv.z, dq[hh].z); dq[hh].w = fmaf(dsv[hh], hv.w, dq[hh].w);
-            }
-          }
+          for (int hh = 0; hh < NH; ++hh) dq[hh] = *reinterpret_cast<const float4*>(slot + hh * E + lane * 4);
           // per-episode accumulators: D0 (t = 0) / D1 (t >= 1) / Dl (IRP)
           float* Dacc = (t == 0 ? p.D0 : p.D1) + b * QW;
           const float lf = s_loadf[m];
@@ -748,7 +704,7 @@ int64_t vrpx_decoder_backward_workspace_bytes(int64_t B, int32_t N) {
   (void)N;
   int64_t grid = (B + TM - 1) / TM;
   if (grid > num_sms()) grid = num_sms();
-  return grid * (int64_t)TM * 3 * QW * (int64_t)sizeof(float);
+  return grid * (int64_t)TM * SCQ * QW * (int64_t)sizeof(float);
 }
 
 int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, const vrpx_decoder_bwd_weights* wb,
