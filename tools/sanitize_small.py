@@ -26,6 +26,17 @@ for (R, K, NOUT) in ((300, 128, 384), (260, 512, 128), (200, 1024, 128)):
     W = torch.randn(NOUT, K, device=dev) / K ** 0.5
     Y = torch.empty(R, NOUT, device=dev)
     vrpx.check(L.vrpx_debug_gemm(vrpx.ptr(X), R, K, vrpx.ptr(W), NOUT, None, 1, None, None, None, vrpx.ptr(Y), 0, vrpx.stream_ptr(dev)))
+# weight-gradient GEMM on tcgen05 (R >= 8192 rows, ragged last block) and the fused in-projection + attention kernel
+A = torch.randn(8192 + 37, 128, device=dev) * 1e-3
+Bm = torch.randn(8192 + 37, 256, device=dev)
+Cw = torch.zeros(128, 256, device=dev)
+vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(Cw), A.shape[0], 128, 256, vrpx.stream_ptr(dev)))
+for (Bq, Nq) in ((37, 50), (9, 21), (5, 100)):
+    X = torch.randn(Bq * Nq, 128, device=dev)
+    W = torch.randn(384, 128, device=dev) / 128 ** 0.5
+    bq = torch.randn(384, device=dev) * 0.1
+    att = torch.empty(Bq * Nq, 128, device=dev)
+    vrpx.check(L.vrpx_debug_qkv_attention(vrpx.ptr(X), vrpx.ptr(W), vrpx.ptr(bq), Bq, Nq, vrpx.ptr(att), vrpx.stream_ptr(dev)))
 torch.cuda.synchronize()
 big = int(os.environ.get("SANITIZE_B", "0"))
 for Env, Agent, N, B in ((TSPEnv, TSPAgent, 12, 40), (VRPEnv, VRPAgent, 9, 24), (IRPEnv, IRPAgent, 10, 24)):
