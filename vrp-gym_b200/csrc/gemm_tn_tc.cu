@@ -12,7 +12,8 @@
 // The kernel is HBM-bound by construction (64 KiB of operands per 786 clocks of MMA), which is the point: the mma.sync
 // kernel it replaces (k_gemm_tn_mma) ran at 45 TFLOP/s, 87 ms of a 611 ms train step at 65,536 x TSP-50.
 // Operand scales: A (a gradient) * 2^12, B (an activation) * 2^8, result * 2^-20; |A| < 16 and |B| < 256 keep f16 finite.
-// Roles (12 warps): 0 TMA producer, 1 MMA issuer, 4-11 converters + accumulator drain.
+// Roles (20 warps): 0 TMA producer, 1 MMA issuer, 4-19 converters + accumulator drain (16 warps: the conversion of a block
+// is a chain of shared-memory reads, conversions and 16-byte stores that eight warps could not keep busy).
 #include "gemm.cuh"
 #include "tc_common.cuh"
 
@@ -21,7 +22,8 @@ namespace tn {
 using namespace tc4;
 
 constexpr int KB = 64;                      // rows per block
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 640;
+constexpr int NCONV = 16;                   // converter warps
 constexpr int W_TMA = 0, W_MMA = 1, W_CONV0 = 4;
 constexpr int RAW_BOX = KB * 128;           // 64 rows x 32 floats = 8 KiB
 constexpr int RAW_OPER = 4 * RAW_BOX;       // 128 columns of one operand = 32 KiB
@@ -57,7 +59,7 @@ __device__ __forceinline__ void mma_f16_ss_w(uint32_t tmem_d, uint64_t adesc, ui
       : "memory")
 
 // one operand of one block: raw [64 rows][128 columns] fp32 (4 SWIZZLE_128B boxes of 32 columns) -> hi / lo tiles
-// [128 columns][64 rows] f16, K-major SWIZZLE_128B.  Thread = (column c, row groups rg0, rg0 + 2, rg0 + 4, rg0 + 6);
+// [128 columns][64 rows] f16, K-major SWIZZLE_128B.  Thread = (column c, row groups rg0, rg0 + 4);
 // the lanes of a warp hold consecutive columns: the raw reads and the 16-byte tile stores are conflict free.
 __device__ __forceinline__ void convert_operand(const unsigned char* raw, unsigned char* hi, unsigned char* lo, int ct, float scale) {
   const int c = ct & 127, rg0 = ct >> 7;
@@ -65,8 +67,8 @@ __device__ __forceinline__ void convert_operand(const unsigned char* raw, unsign
   const int ch = (c & 31) >> 2;
   const int trow = (c >> 3) * 1024 + (c & 7) * 128;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int rg = rg0 + 2 * j;
+  for (int j = 0; j < 2; ++j) {
+    const int rg = rg0 + 4 * j;
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -106,9 +108,9 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (tid == 0) {
     for (int i = 0; i < NRAW; ++i) {
       mbar_init(smem_u32(&s_raw_full[i]), 1);
-      mbar_init(smem_u32(&s_raw_free[i]), 8);
+      mbar_init(smem_u32(&s_raw_free[i]), NCONV);
     }
-    mbar_init(smem_u32(&s_conv_full), 8);
+    mbar_init(smem_u32(&s_conv_full), NCONV);
     mbar_init(smem_u32(&s_conv_free), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -155,15 +157,15 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       mma_commit_w(smem_u32(&s_conv_free));
     }
   } else if (warp >= W_CONV0) {
-    const int cw = warp - W_CONV0, q = warp & 3, chalf = cw >> 2;
-    const int ct = tid - W_CONV0 * 32;   // 0..255
-    float acc[64];
+    const int cw = warp - W_CONV0, q = warp & 3, cq = cw >> 2;   // TMEM lane quarter, 32-column quarter of the accumulator
+    const int ct = tid - W_CONV0 * 32;   // 0..511
+    float acc[32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
     auto drain = [&]() {
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + chalf * 64;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + cq * 32;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < 2; ++b) {
         uint32_t v[16];
         VRPX_TN_LD16(v, taddr + 16 * b);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -195,9 +197,9 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       mbar_wait(smem_u32(&s_conv_free), (uint32_t)((myblk - 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       drain();
-      float* crow = C + (size_t)(mt * 128 + q * 32 + lane) * N + nt * 128 + chalf * 64;
+      float* crow = C + (size_t)(mt * 128 + q * 32 + lane) * N + nt * 128 + cq * 32;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) atomicAdd(crow + j, acc[j] * C_SCALE);
+      for (int j = 0; j < 32; ++j) atomicAdd(crow + j, acc[j] * C_SCALE);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
