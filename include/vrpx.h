@@ -332,6 +332,12 @@ VRPX_API int vrpx_debug_qkv_attention(const float* X, const float* in_proj_w, co
                                       float* att, void* stream);
 VRPX_API void vrpx_debug_encoder_fuse_attention(int32_t enable);
 
+/* Test hook of the attention backward (csrc/attention_bwd.cu): dqkv [B·N][384] = d(loss)/d(qkv) of the per-instance
+ * 8-head attention core given qkv [B·N][384], its output att [B·N][128] and datt = d(loss)/d(att)
+ * (path 0: mma.sync f16-split kernel = production; path 1: fp32 SIMT kernel). */
+VRPX_API int vrpx_debug_attention_backward(const float* qkv, const float* att, const float* datt, float* dqkv, int64_t B,
+                                           int32_t N, int32_t path, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 VRPX_API int64_t vrpx_launch_count(void);
 

@@ -157,13 +157,13 @@ def test_qkv_attention_fused_kernel(B, N):
     assert torch.equal(att, att2)
 
 
-@pytest.mark.parametrize("R,M,N,ascale", [(8192, 128, 128, 1.0), (65536 + 37, 128, 512, 1e-5), (100003, 512, 128, 3e-4),
-                                          (50000, 384, 128, 1e-6), (65536, 1024, 128, 1e-4), (9000, 256, 256, 2.0)])
+@pytest.mark.parametrize("R,M,N,ascale", [(8192, 128, 128, 1.0), (65536 + 37, 128, 512, 1e-5), (100003, 512, 128, 1e-3),
+                                          (50000, 384, 128, 1e-6), (65536, 1024, 128, 1e-2), (9000, 256, 256, 30.0)])
 def test_gemm_tn_tcgen05(R, M, N, ascale):
     """csrc/gemm_tn_tc.cu: the weight-gradient GEMM on tcgen05 (operands transposed and f16-split on the way into shared
-    memory, split-K with register drains) against float64 — O(1) operands and gradient-sized ones (the A operand is
-    scaled by 2^12 before the split: values down to 1e-6 keep fp32-like relative accuracy), ragged row counts, and
-    against the warp-level kernel it replaces."""
+    memory, split-K with register drains) against float64 — O(1) to O(100) operands at 2e-5 of the result scale,
+    gradient-sized ones (below 1e-3 the f16 lo half of the 2^8-scaled operand is a subnormal: about 13 bits at 1e-6) at
+    2e-4, ragged row counts, and against the warp-level kernel it replaces."""
     import vrpx
 
     dev = vrpx.require_device()
@@ -177,7 +177,8 @@ def test_gemm_tn_tcgen05(R, M, N, ascale):
     ref = A.double().T @ Bm.double()
     scale = ref.abs().max().item()
     err = (C.double() - ref).abs().max().item()
-    assert err <= 2e-5 * scale, (R, M, N, err / scale)
+    tol = 2e-5 if ascale >= 1e-3 else 2e-4
+    assert err <= tol * scale, (R, M, N, err / scale)
     L.vrpx_debug_gemm_tn_path(1)
     try:
         C1 = torch.zeros(M, N, device=dev)
@@ -190,4 +191,36 @@ def test_gemm_tn_tcgen05(R, M, N, ascale):
     C2 = C.clone()
     vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(C2), R, M, N, vrpx.stream_ptr(dev)))
     torch.cuda.synchronize()
-    assert (C2.double() - 2 * ref).abs().max().item() <= 4e-5 * scale
+    assert (C2.double() - 2 * ref).abs().max().item() <= 2 * tol * scale
+
+
+@pytest.mark.parametrize("B,N", [(3, 50), (40, 50), (5, 20), (7, 21), (4, 10), (3, 100), (2, 101), (2, 128), (3, 7), (600, 50)])
+def test_attention_backward_mma(B, N):
+    """csrc/attention_bwd.cu: backward of the 8-head attention core on mma.sync (f16 hi/lo halves, both score
+    orientations) against torch autograd in float64, and against the fp32 SIMT kernel it replaces."""
+    import vrpx
+
+    dev = vrpx.require_device()
+    L = vrpx.lib()
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + N)
+    qkv = torch.randn(B * N, 384, generator=g).to(dev)
+    datt = (torch.randn(B * N, 128, generator=g) * 1e-3).to(dev)
+    x = qkv.double().requires_grad_(True)
+    q, k, v = (x.view(B, N, 3, 8, 16)[:, :, i].permute(0, 2, 1, 3) for i in range(3))     # [B][8][N][16]
+    att64 = (torch.softmax(q @ k.transpose(-1, -2) / 4.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * N, 128)
+    (ref,) = torch.autograd.grad(att64, x, datt.double())
+    att = att64.detach().float().contiguous()
+    scale = ref.abs().max().item()
+    outs = []
+    for path in (0, 1):
+        dqkv = torch.full((B * N, 384), float("nan"), device=dev)
+        vrpx.check(L.vrpx_debug_attention_backward(vrpx.ptr(qkv), vrpx.ptr(att), vrpx.ptr(datt), vrpx.ptr(dqkv), B, N, path,
+                                                   vrpx.stream_ptr(dev)))
+        torch.cuda.synchronize()
+        err = (dqkv.double() - ref).abs().max().item()
+        assert err <= 2e-5 * scale, (B, N, path, err / scale)
+        outs.append(dqkv)
+    # each third on its own: dQ, dK, dV
+    for c0 in (0, 128, 256):
+        r = ref[:, c0:c0 + 128]
+        assert (outs[0][:, c0:c0 + 128].double() - r).abs().max().item() <= 2e-5 * r.abs().max().item(), c0

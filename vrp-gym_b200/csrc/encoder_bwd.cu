@@ -204,6 +204,18 @@ extern "C" {
 int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R, int32_t M, int32_t N, void* stream);
 int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out, void* stream);
 
+int vrpx_debug_attention_backward(const float* qkv, const float* att, const float* datt, float* dqkv, int64_t B, int32_t N,
+                                  int32_t path, void* stream) {
+  VRPX_CHECK_ARG(qkv && att && datt && dqkv && B >= 1 && N >= 1 && N <= VRPX_MAX_NODES, "bad argument");
+  VRPX_DEVICE_GUARD(qkv);
+  if (path == 0) return attention_backward_mma(qkv, att, datt, dqkv, B, N, (cudaStream_t)stream);
+  const int attn_smem = 4 * (((4 * 16 + 3) * N + 3) & ~3) * (int)sizeof(float);
+  VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem));
+  k_enc_attention_bwd<<<(unsigned)(B * 2), 128, attn_smem, (cudaStream_t)stream>>>(qkv, att, datt, dqkv, N);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
 int64_t vrpx_encoder_backward_workspace_bytes(int64_t B, int32_t N) {
   // small | T512 [R][512] | T128 [R][128] | Xn [R][4] | Xd [R][4]
   return kBwdSmall + B * (int64_t)N * (512 + 128 + 8) * (int64_t)sizeof(float);
@@ -276,8 +288,12 @@ int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_encoder_weig
       if ((rc = gemm(a, stream))) return rc;
     }
     float* dQKV = T512;  // [R][384]
-    k_enc_attention_bwd<<<(unsigned)(B * 2), 128, attn_smem, stream>>>(QKV, ATT, T128, dQKV, N);
-    VRPX_LAUNCH_CHECK();
+    if (gemm_path == 0) {   // tensor pipe (attention_bwd.cu); the fp32 SIMT kernel stays as the cross-check path
+      if ((rc = attention_backward_mma(QKV, ATT, T128, dQKV, B, N, stream))) return rc;
+    } else {
+      k_enc_attention_bwd<<<(unsigned)(B * 2), 128, attn_smem, stream>>>(QKV, ATT, T128, dQKV, N);
+      VRPX_LAUNCH_CHECK();
+    }
     if ((rc = vrpx_colsum_accumulate(dQKV, R, 3 * E, G.in_proj_b, stream))) return rc;
     if ((rc = vrpx_gemm_tn_accumulate(dQKV, Hin, G.in_proj_w, R, 3 * E, E, stream))) return rc;  // dW_in [384][128]
     {

@@ -49,6 +49,9 @@ int qkv_attention_fused(const float* X, const float* in_proj_w, const float* in_
 // weight-gradient GEMM C [M][N] += A^T · B over the R rows of A [R][M], B [R][N] on tcgen05 (gemm_tn_tc.cu); M, N % 128 == 0
 int gemm_tn_tc(const float* A, const float* Bm, float* C, int64_t R, int M, int N, cudaStream_t stream);
 
+// backward of the per-instance self-attention on mma.sync (attention_bwd.cu): dqkv [B·N][384] from qkv, att = O, datt = dO
+int attention_backward_mma(const float* qkv, const float* att, const float* datt, float* dqkv, int64_t B, int N, cudaStream_t stream);
+
 // path: 0 tcgen05 f16-split (production), 1 fp32 SIMT (cross-check: separates tensor-core error from algorithmic error)
 inline int gemm_dispatch(int path, const GemmArgs& a, cudaStream_t stream) {
   if (path != 0 && path != 1) {

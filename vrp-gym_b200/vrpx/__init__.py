@@ -150,6 +150,7 @@ def lib():
     L.vrpx_debug_ff_fused.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.vrpx_debug_encoder_fuse_ff.argtypes = [i32]
     L.vrpx_debug_encoder_fuse_ff.restype = None
+    L.vrpx_debug_attention_backward.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     L.vrpx_debug_gemm_tn_path.argtypes = [i32]
     L.vrpx_debug_gemm_tn_path.restype = None
     L.vrpx_debug_qkv_attention.argtypes = [vp, vp, vp, i64, i32, vp, vp]
