@@ -303,6 +303,9 @@ VRPX_API int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, 
  * path 1 forces the warp-level mma.sync kernel for every shape (A/B measurements, cross-check in the tests). */
 VRPX_API void vrpx_debug_gemm_tn_path(int32_t path);
 VRPX_API int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out, void* stream);
+/* weight and bias gradient of a linear layer in one call: C += A^T · Bm and colsum_A[M] += column sums of A (may be NULL) */
+VRPX_API int vrpx_gemm_tn_colsum_accumulate(const float* A, const float* Bm, float* C, float* colsum_A, int64_t R, int32_t M,
+                                            int32_t N, void* stream);
 VRPX_API int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B, int32_t N, float* G, float* Xf, void* stream);
 VRPX_API int vrpx_episode_scatter(float* dH, const uint8_t* tape0, int64_t B, int32_t N, const float* dG, const float* dXf,
                                   void* stream);

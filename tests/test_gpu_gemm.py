@@ -187,6 +187,20 @@ def test_gemm_tn_tcgen05(R, M, N, ascale):
     finally:
         L.vrpx_debug_gemm_tn_path(0)
     assert (C1.double() - ref).abs().max().item() <= 2e-5 * scale
+    # bias gradient riding on the weight gradient: column sums of A, on both paths
+    csum_ref = A.double().sum(0)
+    cscale = max(csum_ref.abs().max().item(), A.double().abs().sum(0).max().item() * 1e-3)
+    for path in (0, 1):
+        L.vrpx_debug_gemm_tn_path(path)
+        try:
+            C3, cs = torch.zeros(M, N, device=dev), torch.zeros(M, device=dev)
+            vrpx.check(L.vrpx_gemm_tn_colsum_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(C3), vrpx.ptr(cs), R, M, N,
+                                                        vrpx.stream_ptr(dev)))
+            torch.cuda.synchronize()
+        finally:
+            L.vrpx_debug_gemm_tn_path(0)
+        assert (C3.double() - ref).abs().max().item() <= tol * scale
+        assert (cs.double() - csum_ref).abs().max().item() <= 2e-5 * cscale, (path, R, M)
     # accumulation into a non-zero C
     C2 = C.clone()
     vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(A), vrpx.ptr(Bm), vrpx.ptr(C2), R, M, N, vrpx.stream_ptr(dev)))

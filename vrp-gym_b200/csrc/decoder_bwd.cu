@@ -696,6 +696,48 @@ __global__ void __launch_bounds__(256) k_episode_scatter(float* __restrict__ dH,
 
 }  // namespace vrpx
 
+static int g_tn_path = 0;   // vrpx_debug_gemm_tn_path
+
+namespace vrpx {
+int colsum_launch(const float* X, int64_t R, int Ccols, float* out, cudaStream_t stream) {
+  int64_t ctas = (R + 511) / 512;
+  int64_t maxc = (int64_t)num_sms() * 8;
+  if (ctas > maxc) ctas = maxc;
+  int64_t rows = (R + ctas - 1) / ctas;
+  ctas = (R + rows - 1) / rows;
+  k_colsum_atomic<<<(unsigned)ctas, 256, 0, stream>>>(X, R, Ccols, out, rows);
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+
+int gemm_tn_accumulate(const float* A, const float* Bm, float* C, float* colsum_A, int64_t R, int M, int N, cudaStream_t stream) {
+  // 128-multiples with enough rows to feed every SM: tcgen05 (gemm_tn_tc.cu); the rest (embedding [128][4], tiny batches)
+  // stays on the warp-level kernels
+  if (g_tn_path == 0 && M % 128 == 0 && N % 128 == 0 && R >= 8192 && R <= INT32_MAX &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bm) & 15) == 0)
+    return gemm_tn_tc(A, Bm, C, colsum_A, R, M, N, stream);
+  if (colsum_A) {
+    int rc = colsum_launch(A, R, M, colsum_A, stream);
+    if (rc) return rc;
+  }
+  int64_t ctas = (R + 2047) / 2048;
+  int64_t maxc = (int64_t)num_sms() * 8;
+  if (ctas > maxc) ctas = maxc;
+  int64_t rows = ((R + ctas - 1) / ctas + 15) / 16 * 16;
+  ctas = (R + rows - 1) / rows;
+  dim3 grid((unsigned)ctas, (unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+  if (M % 64 == 0 && N % 64 == 0) {
+    rows = (rows + 31) / 32 * 32;
+    grid.x = (unsigned)((R + rows - 1) / rows);
+    k_gemm_tn_mma<<<grid, 128, 0, stream>>>(A, Bm, C, R, M, N, rows);
+  } else {
+    k_gemm_tn_atomic<<<grid, 256, 0, stream>>>(A, Bm, C, R, M, N, rows);
+  }
+  VRPX_LAUNCH_CHECK();
+  return VRPX_OK;
+}
+}  // namespace vrpx
+
 using namespace vrpx;
 
 extern "C" {
@@ -739,45 +781,25 @@ int vrpx_decoder_backward(const vrpx_env* env, const vrpx_decoder_weights* w, co
   return VRPX_OK;
 }
 
-static int g_tn_path = 0;   // vrpx_debug_gemm_tn_path
 void vrpx_debug_gemm_tn_path(int32_t path) { g_tn_path = path; }
 
 int vrpx_gemm_tn_accumulate(const float* A, const float* Bm, float* C, int64_t R, int32_t M, int32_t N, void* stream) {
   VRPX_CHECK_ARG(A && Bm && C && R >= 1 && M >= 1 && N >= 1 && M % 4 == 0 && N % 4 == 0, "bad argument");
   VRPX_DEVICE_GUARD(A);
-  // 128-multiples with enough rows to feed every SM: tcgen05 (gemm_tn_tc.cu); the rest (embedding [128][4], tiny batches)
-  // stays on the warp-level kernels below
-  if (g_tn_path == 0 && M % 128 == 0 && N % 128 == 0 && R >= 8192 && R <= INT32_MAX &&
-      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bm) & 15) == 0)
-    return gemm_tn_tc(A, Bm, C, R, M, N, (cudaStream_t)stream);
-  int64_t ctas = (R + 2047) / 2048;
-  int64_t maxc = (int64_t)num_sms() * 8;
-  if (ctas > maxc) ctas = maxc;
-  int64_t rows = ((R + ctas - 1) / ctas + 15) / 16 * 16;
-  ctas = (R + rows - 1) / rows;
-  dim3 grid((unsigned)ctas, (unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
-  if (M % 64 == 0 && N % 64 == 0) {
-    rows = (rows + 31) / 32 * 32;
-    grid.x = (unsigned)((R + rows - 1) / rows);
-    k_gemm_tn_mma<<<grid, 128, 0, (cudaStream_t)stream>>>(A, Bm, C, R, M, N, rows);
-  } else {
-    k_gemm_tn_atomic<<<grid, 256, 0, (cudaStream_t)stream>>>(A, Bm, C, R, M, N, rows);
-  }
-  VRPX_LAUNCH_CHECK();
-  return VRPX_OK;
+  return gemm_tn_accumulate(A, Bm, C, nullptr, R, M, N, (cudaStream_t)stream);
+}
+
+int vrpx_gemm_tn_colsum_accumulate(const float* A, const float* Bm, float* C, float* colsum_A, int64_t R, int32_t M, int32_t N,
+                                    void* stream) {
+  VRPX_CHECK_ARG(A && Bm && C && R >= 1 && M >= 1 && N >= 1 && M % 4 == 0 && N % 4 == 0, "bad argument");
+  VRPX_DEVICE_GUARD(A);
+  return gemm_tn_accumulate(A, Bm, C, colsum_A, R, M, N, (cudaStream_t)stream);
 }
 
 int vrpx_colsum_accumulate(const float* X, int64_t R, int32_t Ccols, float* out, void* stream) {
   VRPX_CHECK_ARG(X && out && R >= 1 && Ccols >= 1, "bad argument");
   VRPX_DEVICE_GUARD(X);
-  int64_t ctas = (R + 511) / 512;
-  int64_t maxc = (int64_t)num_sms() * 8;
-  if (ctas > maxc) ctas = maxc;
-  int64_t rows = (R + ctas - 1) / ctas;
-  ctas = (R + rows - 1) / rows;
-  k_colsum_atomic<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(X, R, Ccols, out, rows);
-  VRPX_LAUNCH_CHECK();
-  return VRPX_OK;
+  return colsum_launch(X, R, Ccols, out, (cudaStream_t)stream);
 }
 
 int vrpx_episode_gather(const float* h, const uint8_t* tape0, int64_t B, int32_t N, float* G, float* Xf, void* stream) {

@@ -261,15 +261,13 @@ int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_encoder_weig
                                                 G.bn2_w, G.bn2_b);
     VRPX_LAUNCH_CHECK();
     // ---- FF backward:  y2 = h1 + relu(h1 W1^T + b1) W2^T + b2
-    if ((rc = vrpx_colsum_accumulate(g, R, E, G.ff2_b, stream))) return rc;
-    if ((rc = vrpx_gemm_tn_accumulate(g, F, G.ff2_w, R, E, FF, stream))) return rc;          // dW2 [128][512] += dy2^T F
+    if ((rc = gemm_tn_accumulate(g, F, G.ff2_w, G.ff2_b, R, E, FF, stream))) return rc;       // dW2 [128][512] += dy2^T F, db2 += colsum(dy2)
     {
       GemmArgs a{g, R, E, LT.ff2_wT, FF, nullptr, 0, nullptr, nullptr, nullptr, T512};        // dpre = (dy2 W2) * [F > 0]
       a.gate = F;
       if ((rc = gemm(a, stream))) return rc;
     }
-    if ((rc = vrpx_colsum_accumulate(T512, R, FF, G.ff0_b, stream))) return rc;
-    if ((rc = vrpx_gemm_tn_accumulate(T512, H1, G.ff0_w, R, FF, E, stream))) return rc;      // dW1 [512][128] += dpre^T h1
+    if ((rc = gemm_tn_accumulate(T512, H1, G.ff0_w, G.ff0_b, R, FF, E, stream))) return rc;   // dW1 [512][128] += dpre^T h1, db1
     {
       GemmArgs a{T512, R, FF, LT.ff0_wT, E, nullptr, 0, g, nullptr, nullptr, g};              // dh1 = dy2 + dpre W1
       if ((rc = gemm(a, stream))) return rc;
@@ -281,8 +279,7 @@ int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_encoder_weig
                                                 G.bn1_b);
     VRPX_LAUNCH_CHECK();
     // ---- attention block backward:  y1 = x + att W_o^T + b_o,  att = MHA_core(x W_in^T + b_in)
-    if ((rc = vrpx_colsum_accumulate(g, R, E, G.out_proj_b, stream))) return rc;
-    if ((rc = vrpx_gemm_tn_accumulate(g, ATT, G.out_proj_w, R, E, E, stream))) return rc;    // dW_o += dy1^T att
+    if ((rc = gemm_tn_accumulate(g, ATT, G.out_proj_w, G.out_proj_b, R, E, E, stream))) return rc;   // dW_o += dy1^T att, db_o
     {
       GemmArgs a{g, R, E, LT.out_proj_wT, E, nullptr, 0, nullptr, nullptr, nullptr, T128};    // datt = dy1 W_o
       if ((rc = gemm(a, stream))) return rc;
@@ -294,8 +291,7 @@ int vrpx_encoder_backward(const vrpx_encoder_weights* w, const vrpx_encoder_weig
       k_enc_attention_bwd<<<(unsigned)(B * 2), 128, attn_smem, stream>>>(QKV, ATT, T128, dQKV, N);
       VRPX_LAUNCH_CHECK();
     }
-    if ((rc = vrpx_colsum_accumulate(dQKV, R, 3 * E, G.in_proj_b, stream))) return rc;
-    if ((rc = vrpx_gemm_tn_accumulate(dQKV, Hin, G.in_proj_w, R, 3 * E, E, stream))) return rc;  // dW_in [384][128]
+    if ((rc = gemm_tn_accumulate(dQKV, Hin, G.in_proj_w, G.in_proj_b, R, 3 * E, E, stream))) return rc;   // dW_in [384][128], db_in
     {
       GemmArgs a{dQKV, R, 3 * E, LT.in_proj_wT, E, nullptr, 0, g, nullptr, nullptr, g};       // dx = dy1 + dqkv W_in
       if ((rc = gemm(a, stream))) return rc;

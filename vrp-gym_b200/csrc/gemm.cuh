@@ -47,7 +47,10 @@ int qkv_attention_fused(const float* X, const float* in_proj_w, const float* in_
                         cudaStream_t stream);
 
 // weight-gradient GEMM C [M][N] += A^T · B over the R rows of A [R][M], B [R][N] on tcgen05 (gemm_tn_tc.cu); M, N % 128 == 0
-int gemm_tn_tc(const float* A, const float* Bm, float* C, int64_t R, int M, int N, cudaStream_t stream);
+int gemm_tn_tc(const float* A, const float* Bm, float* C, float* colsum_A, int64_t R, int M, int N, cudaStream_t stream);
+// C += A^T · B and (optional) colsum_A [M] += column sums of A, through gemm_tn_tc when the shape allows, else the warp-level
+// kernels of decoder_bwd.cu (the bias gradient of a linear layer rides on its weight-gradient GEMM)
+int gemm_tn_accumulate(const float* A, const float* Bm, float* C, float* colsum_A, int64_t R, int M, int N, cudaStream_t stream);
 
 // backward of the per-instance self-attention on mma.sync (attention_bwd.cu): dqkv [B·N][384] from qkv, att = O, datt = dO
 int attention_backward_mma(const float* qkv, const float* att, const float* datt, float* dqkv, int64_t B, int N, cudaStream_t stream);

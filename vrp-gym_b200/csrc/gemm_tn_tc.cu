@@ -61,7 +61,9 @@ __device__ __forceinline__ void mma_f16_ss_w(uint32_t tmem_d, uint64_t adesc, ui
 // one operand of one block: raw [64 rows][128 columns] fp32 (4 SWIZZLE_128B boxes of 32 columns) -> hi / lo tiles
 // [128 columns][64 rows] f16, K-major SWIZZLE_128B.  Thread = (column c, row groups rg0, rg0 + 4);
 // the lanes of a warp hold consecutive columns: the raw reads and the 16-byte tile stores are conflict free.
-__device__ __forceinline__ void convert_operand(const unsigned char* raw, unsigned char* hi, unsigned char* lo, int ct, float scale) {
+// `csum` (optional) collects the sum of the thread's scaled values: the column sums of A are the bias gradient.
+__device__ __forceinline__ void convert_operand(const unsigned char* raw, unsigned char* hi, unsigned char* lo, int ct, float scale,
+                                                float* csum = nullptr) {
   const int c = ct & 127, rg0 = ct >> 7;
   const unsigned char* rb = raw + (c >> 5) * RAW_BOX + (c & 3) * 4;
   const int ch = (c & 31) >> 2;
@@ -75,6 +77,7 @@ __device__ __forceinline__ void convert_operand(const unsigned char* raw, unsign
       const int row = 8 * rg + i;
       x[i] = *reinterpret_cast<const float*>(rb + row * 128 + ((ch ^ (row & 7)) << 4)) * scale;
     }
+    if (csum) *csum += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -91,8 +94,8 @@ __device__ __forceinline__ void convert_operand(const unsigned char* raw, unsign
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C, int64_t R,
-             int M, int N) {
+k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C,
+             float* __restrict__ colsum, int64_t R, int M, int N) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t s_raw_full[NRAW], s_raw_free[NRAW], s_conv_full, s_conv_free;
   __shared__ uint32_t s_tmem;
@@ -162,6 +165,9 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    // column sums of A (= the bias gradient when A is dY): the CTAs of the first column tile see every row of A once
+    const bool want_sum = colsum != nullptr && nt == 0;
+    float csum = 0.f;
     auto drain = [&]() {
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + cq * 32;
 #pragma unroll
@@ -183,7 +189,7 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if ((i % DRAIN) == 0) drain();
       }
       const unsigned char* raw = smem + SM_RAW + rs * RAW_BLOCK;
-      convert_operand(raw, smem + SM_AH, smem + SM_AL, ct, A_SCALE);
+      convert_operand(raw, smem + SM_AH, smem + SM_AL, ct, A_SCALE, want_sum ? &csum : nullptr);
       convert_operand(raw + RAW_OPER, smem + SM_BH, smem + SM_BL, ct, B_SCALE);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -201,6 +207,7 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
       for (int j = 0; j < 32; ++j) atomicAdd(crow + j, acc[j] * C_SCALE);
     }
+    if (want_sum) atomicAdd(colsum + mt * 128 + (ct & 127), csum * (1.0f / A_SCALE));
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -211,8 +218,9 @@ k_gemm_tn_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
 }  // namespace tn
 
-// C [M][N] += A^T · B on tcgen05; M and N multiples of 128, A and B 16-byte aligned row-major [R][M], [R][N]
-int gemm_tn_tc(const float* A, const float* Bm, float* C, int64_t R, int M, int N, cudaStream_t stream) {
+// C [M][N] += A^T · B on tcgen05; M and N multiples of 128, A and B 16-byte aligned row-major [R][M], [R][N];
+// colsum_A (optional) [M] += column sums of A
+int gemm_tn_tc(const float* A, const float* Bm, float* C, float* colsum_A, int64_t R, int M, int N, cudaStream_t stream) {
   using namespace tn;
   if (M % 128 || N % 128 || R < 1 || R > (int64_t)INT32_MAX) {
     set_error("gemm_tn_tc: bad shape");
@@ -228,7 +236,7 @@ int gemm_tn_tc(const float* A, const float* Bm, float* C, int64_t R, int M, int 
   if (nsplit > nblk) nsplit = nblk;
   if (nsplit < 1) nsplit = 1;
   VRPX_CUDA(cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  k_gemm_tn_tc<<<(unsigned)(nsplit * P), NTHREADS, SMEM_BYTES, stream>>>(ma, mb, C, R, M, N);
+  k_gemm_tn_tc<<<(unsigned)(nsplit * P), NTHREADS, SMEM_BYTES, stream>>>(ma, mb, C, colsum_A, R, M, N);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
 }

@@ -127,6 +127,7 @@ def lib():
     L.vrpx_decoder_backward.argtypes = [C.POINTER(EnvView), C.POINTER(DecoderWeights), C.POINTER(DecoderBwdWeights), vp, vp,
                                         i32, i64, C.POINTER(RolloutTrace), vp, vp, C.POINTER(DecoderGrads), vp, i64, vp]
     L.vrpx_gemm_tn_accumulate.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+    L.vrpx_gemm_tn_colsum_accumulate.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     L.vrpx_colsum_accumulate.argtypes = [vp, i64, i32, vp, vp]
     L.vrpx_episode_gather.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.vrpx_episode_scatter.argtypes = [vp, vp, i64, i32, vp, vp, vp]
