@@ -41,6 +41,26 @@ def _gemm_nt(X, W, residual=None, path=0):
     return Y
 
 
+# The f16 hi/lo split of the tensor-core GEMMs (f16split.cuh) scales its operands by 2^8: values below ~1e-4 leave their lo
+# halves in the f16 subnormals and values above 255 overflow.  Per-row gradients of a mean loss shrink with the batch
+# (1e-5 ... 1e-7 at 65,536 instances: 0.3 % ... 24 % error in the encoder gradients, tools/grad_scale_probe.py), so the
+# encoder backward runs on dH * 2^k with max|dH| * 2^k = 2^-6 — every op of the backward is linear in dH, a power of two
+# is exact, and the 2^14 of headroom covers what BatchNorm and the projections can amplify — and the parameter
+# gradients are scaled back before they are accumulated.
+_GRAD_TARGET_LOG2 = -6
+_GRAD_TARGET_ENV = None   # tools/grad_scale_probe.py overrides the target for its sweep
+
+
+def _grad_gain(dH, target_log2=None):
+    amax = float(dH.abs().amax())
+    if not (amax > 0.0) or amax == float("inf") or amax != amax:
+        return 1.0
+    if target_log2 is None:
+        target_log2 = _GRAD_TARGET_LOG2 if _GRAD_TARGET_ENV is None else _GRAD_TARGET_ENV
+    k = target_log2 - math.frexp(amax)[1]          # amax = m * 2^e with 0.5 <= m < 1: amax * 2^k in [2^-7, 2^-6)
+    return 2.0 ** max(-60, min(60, k))
+
+
 def decoder_backward(dec, env, h, roll, wts, gemm_path=0):
     """Back-propagate wts[b] = dL/d(logp_b) through the rollout `roll` (dict from GraphDecoder.rollout_episode with
     save_for_backward=True).  Accumulates the decoder parameters' .grad and returns dL/dh (B,N,128)."""
@@ -69,17 +89,28 @@ def decoder_backward(dec, env, h, roll, wts, gemm_path=0):
                                        int(roll["coupling"]), C.byref(trace), vrpx.ptr(sv["qg"]), vrpx.ptr(wts),
                                        C.byref(gs), vrpx.ptr(ws), nbytes, st))
     # ---- per-episode terms: q~ also contains A_g·g + a_c (every step), A_f·h[first] (steps >= 1), a_q0 (step 0)
+    # the per-episode sums D are gradients too: the two products below that run on the f16-split tensor-core kernels get
+    # them scaled to 2^-2 (see _grad_gain; the sums are final, nothing amplifies them further) and are scaled back
     Dsum = g["D0"] + g["D1"]
+    gs_, g1_ = (_grad_gain(Dsum, -2), _grad_gain(g["D1"], -2)) if gemm_path == 0 else (1.0, 1.0)
+    DsumS = Dsum * gs_ if gs_ != 1.0 else Dsum
+    D1S = g["D1"] * g1_ if g1_ != 1.0 else g["D1"]
     G = torch.empty((B, 128), dtype=torch.float32, device=dev)
     Xf = None if irp else torch.empty((B, 128), dtype=torch.float32, device=dev)
     tape0 = tape[0].contiguous()
     vrpx.check(L.vrpx_episode_gather(vrpx.ptr(h), vrpx.ptr(tape0), B, N, vrpx.ptr(G), vrpx.ptr(Xf) if Xf is not None else None, st))
-    dG = _gemm_nt(Dsum, tens["ag_t"], path=gemm_path)                      # (B,128) = Dsum · A_g
-    dXf = None if irp else _gemm_nt(g["D1"], tens["af_t"], path=gemm_path)  # (B,128) = D1 · A_f
+    dG = _gemm_nt(DsumS, tens["ag_t"], path=gemm_path)                      # (B,128) = Dsum · A_g
+    dXf = None if irp else _gemm_nt(D1S, tens["af_t"], path=gemm_path)       # (B,128) = D1 · A_f
+    if gs_ != 1.0:
+        dG.mul_(1.0 / gs_)
+    if dXf is not None and g1_ != 1.0:
+        dXf.mul_(1.0 / g1_)
     vrpx.check(L.vrpx_episode_scatter(vrpx.ptr(g["dH"]), vrpx.ptr(tape0), B, N, vrpx.ptr(dG),
                                       vrpx.ptr(dXf) if dXf is not None else None, st))
     grads = {"al_t": g["d_al_t"], "m_t": g["d_m_t"], "m_c": g["d_m_c"], "ag_t": z(128, 1024), "a_c": z(1024), "a_q0": z(1024)}
-    vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(G), vrpx.ptr(Dsum), vrpx.ptr(grads["ag_t"]), B, 128, 1024, st))
+    vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(G), vrpx.ptr(DsumS), vrpx.ptr(grads["ag_t"]), B, 128, 1024, st))
+    if gs_ != 1.0:
+        grads["ag_t"].mul_(1.0 / gs_)
     vrpx.check(L.vrpx_colsum_accumulate(vrpx.ptr(Dsum), B, 1024, vrpx.ptr(grads["a_c"]), st))
     vrpx.check(L.vrpx_colsum_accumulate(vrpx.ptr(g["D0"]), B, 1024, vrpx.ptr(grads["a_q0"]), st))
     if irp:
@@ -87,7 +118,9 @@ def decoder_backward(dec, env, h, roll, wts, gemm_path=0):
         vrpx.check(L.vrpx_colsum_accumulate(vrpx.ptr(g["Dl"]), B, 1024, vrpx.ptr(grads["a_load"]), st))
     else:
         grads["af_t"] = z(128, 1024)
-        vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(Xf), vrpx.ptr(g["D1"]), vrpx.ptr(grads["af_t"]), B, 128, 1024, st))
+        vrpx.check(L.vrpx_gemm_tn_accumulate(vrpx.ptr(Xf), vrpx.ptr(D1S), vrpx.ptr(grads["af_t"]), B, 128, 1024, st))
+        if g1_ != 1.0:
+            grads["af_t"].mul_(1.0 / g1_)
     # ---- pull the packed-array gradients back to the module parameters (tiny weight-only products)
     params = [p for p in dec.parameters() if p.requires_grad]
     with torch.enable_grad():
@@ -102,24 +135,6 @@ def decoder_backward(dec, env, h, roll, wts, gemm_path=0):
         if gp is not None:
             _acc_grad(p, gp)
     return g["dH"]
-
-
-# The f16 hi/lo split of the tensor-core GEMMs (f16split.cuh) scales its operands by 2^8: values below ~1e-4 leave their lo
-# halves in the f16 subnormals and values above 255 overflow.  Per-row gradients of a mean loss shrink with the batch
-# (1e-5 ... 1e-7 at 65,536 instances: 0.3 % ... 24 % error in the encoder gradients, tools/grad_scale_probe.py), so the
-# encoder backward runs on dH * 2^k with max|dH| * 2^k = 2^-6 — every op of the backward is linear in dH, a power of two
-# is exact, and the 2^14 of headroom covers what BatchNorm and the projections can amplify — and the parameter
-# gradients are scaled back before they are accumulated.
-_GRAD_TARGET_LOG2 = -6
-_GRAD_TARGET_ENV = None   # tools/grad_scale_probe.py overrides the target for its sweep
-
-
-def _grad_gain(dH):
-    amax = float(dH.abs().amax())
-    if not (amax > 0.0) or amax == float("inf") or amax != amax:
-        return 1.0
-    k = (_GRAD_TARGET_LOG2 if _GRAD_TARGET_ENV is None else _GRAD_TARGET_ENV) - math.frexp(amax)[1]          # amax = m * 2^e with 0.5 <= m < 1: amax * 2^k in [2^-7, 2^-6)
-    return 2.0 ** max(-60, min(60, k))
 
 
 def encoder_backward(enc, env, depot, saved, dH, gemm_path=0):
