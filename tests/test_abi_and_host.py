@@ -170,3 +170,40 @@ def test_f16_hi_lo_split_keeps_fp32_accuracy(scale):
     assert np.max(np.abs(got - ref)) < 2e-6 * np.abs(ref).max()
     # a single f16 (or TF32) pass would miss the bar by three orders of magnitude
     assert np.max(np.abs(f(xh) @ f(wh) - ref)) > 1e-4 * np.abs(ref).max()
+
+
+def test_gradient_gain_is_an_exact_power_of_two_in_range():
+    """vrpx/backward.py::_grad_gain: the gain that brings a gradient tensor into the range of the f16-split GEMMs is a
+    power of two (exact to apply and to undo), puts the largest element in [2^(t-1), 2^t), and is 1 for empty / zero /
+    non-finite inputs; the numpy restatement of the split shows what it buys: a 1e-6-sized operand keeps ~13 bits
+    unscaled (2^8 only) and ~21 bits with the gain."""
+    import math
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "vrp-gym_b200"))
+    from vrpx import backward as vb
+
+    rs = np.random.RandomState(1)
+    for mag in (1e-9, 3e-6, 0.02, 1.0, 77.0, 5e4):
+        t = torch.from_numpy((rs.randn(64, 128) * mag).astype(np.float32))
+        for target in (-6, -2):
+            g = vb._grad_gain(t, target)
+            assert math.frexp(g)[0] == 0.5                                        # a power of two
+            top = float(t.abs().max()) * g
+            assert 2.0 ** (target - 1) <= top < 2.0 ** target, (mag, target, top)
+    assert vb._grad_gain(torch.zeros(4, 4)) == 1.0
+    assert vb._grad_gain(torch.tensor([float("nan"), 1.0])) == 1.0
+    assert vb._grad_gain(torch.tensor([float("inf"), 1.0])) == 1.0
+    # what the gain buys, on the numpy restatement of the operand split (scale 2^8, unscaled lo half)
+    x = (rs.randn(4096) * 1e-6).astype(np.float32)
+
+    def rel_err(v):
+        s = v * np.float32(256.0)
+        hi, lo = _split_f16(s, 1.0)
+        rec = hi.astype(np.float64) + lo.astype(np.float64)
+        big = np.abs(v) > 0.1 * np.abs(v).max()
+        return np.max(np.abs(rec - s)[big] / np.abs(s)[big])
+
+    g = vb._grad_gain(torch.from_numpy(x))
+    assert rel_err(x) > 2.0 ** -15                       # ~13 bits: the lo half is a subnormal
+    assert rel_err(x * np.float32(g)) < 2.0 ** -17       # the gain moves it back into the normal range
