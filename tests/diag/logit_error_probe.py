@@ -1,5 +1,9 @@
-import sys, os
-sys.path[:0] = ["/root/repo/vrp-gym_b200", "/root/repo"]
+"""Worst gap between the CUDA logits and the oracle at the chosen action, classic vs table mode (diagnostic, GPU box)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [os.path.join(ROOT, "vrp-gym_b200"), ROOT]
 import numpy as np, torch
 from agents import VRPAgent, TSPAgent
 from gym_vrp.envs import VRPEnv, TSPEnv

@@ -3,7 +3,7 @@
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (os.path.join(ROOT, "vrp-gym_b200"), ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np
