@@ -57,7 +57,7 @@ __device__ __forceinline__ void frag_from_c(const float (&c0)[4], const float (&
 }
 
 template <int NK8>
-__global__ void __launch_bounds__(256) k_enc_attention_bwd_mma(const float* __restrict__ qkv, const float* __restrict__ att,
+__global__ void __launch_bounds__(256, (NK8 <= 8) ? 3 : 1) k_enc_attention_bwd_mma(const float* __restrict__ qkv, const float* __restrict__ att,
                                                                 const float* __restrict__ datt, float* __restrict__ dqkv, int N) {
   using LT = Layout<NK8>;
   constexpr int NJJ = LT::NJJ, NP = LT::NP, VDS = LT::VDS;
@@ -286,6 +286,8 @@ template <int NK8>
 static int launch(const float* qkv, const float* att, const float* datt, float* dqkv, int64_t B, int N, cudaStream_t stream) {
   constexpr int smem = Layout<NK8>::SMEM;
   VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_bwd_mma<NK8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // three CTAs per SM at N <= 64 (64.5 KiB each): ask for the largest shared-memory carve-out
+  VRPX_CUDA(cudaFuncSetAttribute(k_enc_attention_bwd_mma<NK8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   k_enc_attention_bwd_mma<NK8><<<(unsigned)(B * 4), 256, smem, stream>>>(qkv, att, datt, dqkv, N);
   VRPX_LAUNCH_CHECK();
   return VRPX_OK;
